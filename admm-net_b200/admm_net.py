@@ -1,0 +1,207 @@
+"""Drop-in mirror of the reference's `admm_net` module API for the unrolled forward path.
+
+Same constructor signatures, attribute names and `state_dict` keys as /root/reference/admm_net.py
+(PhiLayer 71-105, HLayer 108-205, GLayer 208-354, ZLayer 357-490, PhiEstADMMNet 724-764), so
+`load_state_dict(checkpoint['model_state_dict'])` accepts reference checkpoints and optimiser param
+groups that match on 'phiLayers'/'hLayers'/'gLayers'/'zLayers' (trainPhi.py:106-111) keep working.
+The layer modules only HOLD parameters; the arithmetic of `PhiEstADMMNet.forward` runs in the sm_100a
+kernels behind include/admmnet_b200.h (no PyTorch/CPU fallback).
+
+Differences from the reference, all documented in DESIGN.md:
+  * forward is an inference fast path: the result carries no autograd graph;
+  * `norm_scope` / `chunk` attributes control how the ZLayer batch mean (admm_net.py:459) is scoped:
+      'batch' (default) = the whole batch of the call, exactly like the reference;
+      'chunk'           = independent chunks of `chunk` signals (throughput mode, no coupling);
+  * `ADMMNet`'s learned PeakSearchLayer head (admm_net.py:494-720) is not part of this round's hot path.
+"""
+import ctypes as C
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _capi
+from .params import pack_state_dict, param_stride
+
+
+class PhiLayer(nn.Module):
+    """Parameter holder for admm_net.py:71-105."""
+
+    def __init__(self, epsilon=1e-8):
+        super().__init__()
+        self.rho = nn.Parameter(torch.tensor(1.0))
+        self.epsilon = epsilon
+
+
+class HLayer(nn.Module):
+    """Parameter holder for admm_net.py:108-205."""
+
+    def __init__(self, M, N, epsilon=1e-8):
+        super().__init__()
+        self.M, self.N = M, N
+        self.dim = M * N
+        self.epsilon = epsilon
+        self.rho = nn.Parameter(torch.tensor(1.0))
+        self.projection_weight = nn.Parameter(torch.tensor(1.0))
+        self.correction_net = nn.Sequential(nn.Linear(self.dim, 64), nn.ReLU(), nn.Linear(64, self.dim), nn.Tanh())
+
+
+class GLayer(nn.Module):
+    """Parameter holder for admm_net.py:208-354."""
+
+    def __init__(self, M, N, epsilon=1e-8, use_learnable_threshold=True):
+        super().__init__()
+        self.M, self.N = M, N
+        self.dim = M * N + 1
+        self.epsilon = epsilon
+        self.lambda_param = nn.Parameter(torch.tensor(0.1))
+        self.rho = nn.Parameter(torch.tensor(1.0))
+        if use_learnable_threshold:
+            self.threshold = nn.Parameter(torch.tensor(0.0))
+        else:
+            self.threshold = torch.tensor(0.0)
+        self.value_net = nn.Sequential(nn.Linear(1, 16), nn.ReLU(), nn.Linear(16, 1), nn.Sigmoid())
+
+
+class ZLayer(nn.Module):
+    """Parameter holder for admm_net.py:357-490 (step_adjust_net exists in the state_dict, is never used)."""
+
+    def __init__(self, M, N, epsilon=1e-8):
+        super().__init__()
+        self.M, self.N = M, N
+        self.dim_h = M * N
+        self.dim_z = M * N + 1
+        self.epsilon = epsilon
+        self.rho = nn.Parameter(torch.tensor(1.0))
+        self.lambda_param = nn.Parameter(torch.tensor(1.0))
+        self.residual_scale_net = nn.Sequential(nn.Linear(3, 32), nn.ReLU(), nn.Linear(32, 1), nn.Sigmoid())
+        self.step_adjust_net = nn.Sequential(nn.Linear(3, 8), nn.ReLU(), nn.Linear(8, 1), nn.Sigmoid())
+
+
+class _Workspace:
+    """Caller-owned device buffers for one (B, chunk, n, K, rcap) configuration."""
+
+    def __init__(self, B, chunk, n, K, rcap, device):
+        L = _capi.lib()
+        nbytes = C.c_size_t()
+        _capi.check(L.admmnet_forward_workspace_bytes(B, chunk, n, K, rcap, C.byref(nbytes)))
+        self.key = (B, chunk, n, K, rcap, str(device))
+        self.nbytes = nbytes.value
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.B, self.chunk, self.n, self.K, self.rcap = B, chunk, n, K, rcap
+        rs, mn, stt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _capi.check(L.admmnet_ws_scalars(self.ptr, self.nbytes, B, chunk, n, K, rcap, C.byref(rs), C.byref(mn),
+                                         C.byref(stt)))
+        base = self.buf.data_ptr()
+        self.rsum = self.buf[rs.value - base: rs.value - base + 8 * (K + 1)].view(torch.float64)
+        self.mean = self.buf[mn.value - base: mn.value - base + 4 * (K + 1)].view(torch.float32)
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+class PhiEstADMMNet(nn.Module):
+    """admm_net.py:724-764.  forward(y, b, sigma) -> phi  (complex64 [B, M*N])."""
+
+    default_chunk = 16384
+
+    def __init__(self, M, N, L=3, num_layers=10):
+        super().__init__()
+        self.num_layers = num_layers
+        self.M, self.N, self.L = M, N, L
+        self.phiLayers = nn.ModuleList([PhiLayer() for _ in range(num_layers)])
+        self.hLayers = nn.ModuleList([HLayer(M, N) for _ in range(num_layers)])
+        self.gLayers = nn.ModuleList([GLayer(M, N) for _ in range(num_layers)])
+        self.zLayers = nn.ModuleList([ZLayer(M, N) for _ in range(num_layers)])
+        self.norm_scope = "batch"
+        self.chunk = self.default_chunk
+        self.rcap = 0
+        self.check_status = True
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+        self._warned = False
+
+    # ------------------------------------------------------------------ parameters
+    def packed_params(self, device):
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._packed_key != key:
+            self._packed = pack_state_dict(self.state_dict(), self.M * self.N, self.num_layers).to(device)
+            self._packed_key = key
+        return self._packed
+
+    def workspace(self, B, chunk, device):
+        n, K = self.M * self.N, self.num_layers
+        key = (B, chunk, n, K, self.rcap, str(device))
+        if self._ws is None or self._ws.key != key:
+            self._ws = None
+            self._ws = _Workspace(B, chunk, n, K, self.rcap, device)
+        return self._ws
+
+    # ------------------------------------------------------------------ forward
+    def _prep(self, y, b, sigma):
+        if y.dim() != 2 or y.shape != b.shape or y.shape[1] != self.M * self.N:
+            raise ValueError(f"y and b must be [B, {self.M * self.N}] (got {tuple(y.shape)}, {tuple(b.shape)})")
+        B = y.shape[0]
+        if sigma.numel() != B:
+            raise ValueError("sigma must hold one value per signal ([B] or [B,1])")
+        _capi.require_cuda()
+        dev = y.device if y.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        to = lambda t, dt: t.detach().to(device=dev, dtype=dt, non_blocking=True).contiguous()
+        return to(y, torch.complex64), to(b, torch.complex64), to(sigma.reshape(-1), torch.float32), dev
+
+    def forward_device(self, y, b, sigma, out=None):
+        """Device-resident fast path: y,b complex64 [B,n] and sigma float32 [B] already on the GPU."""
+        L = _capi.lib()
+        B, n, K = y.shape[0], self.M * self.N, self.num_layers
+        dev = y.device
+        P = self.packed_params(dev)
+        if out is None:
+            out = torch.empty(B, n, dtype=torch.complex64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        chunk = min(self.chunk, B)
+        if self.norm_scope == "batch":
+            ws = self.workspace(B, chunk, dev)
+            _capi.check(L.admmnet_forward(y.data_ptr(), b.data_ptr(), sigma.data_ptr(), B, chunk, self.M, self.N, K,
+                                          P.data_ptr(), out.data_ptr(), ws.ptr, ws.nbytes, self.rcap, stream))
+            self._status(ws, stream)
+        elif self.norm_scope == "chunk":
+            for off in range(0, B, chunk):
+                Bc = min(chunk, B - off)
+                ws = self.workspace(Bc, Bc, dev)
+                _capi.check(L.admmnet_forward(y[off:].data_ptr(), b[off:].data_ptr(), sigma[off:].data_ptr(), Bc, Bc,
+                                              self.M, self.N, K, P.data_ptr(), out[off:].data_ptr(), ws.ptr, ws.nbytes,
+                                              self.rcap, stream))
+                self._status(ws, stream)
+        else:
+            raise ValueError("norm_scope must be 'batch' or 'chunk' (use sharding.sharded_forward for 'global')")
+        return out
+
+    def _status(self, ws, stream):
+        if not self.check_status:
+            return
+        st = C.c_int(0)
+        _capi.check(_capi.lib().admmnet_status(ws.ptr, ws.nbytes, ws.B, ws.chunk, ws.n, ws.K, ws.rcap, stream,
+                                               C.byref(st)))
+        if st.value:
+            raise _capi.AdmmnetError(f"eigen-solver reported status {st.value} (QL non-convergence / stream overflow)")
+
+    def forward(self, y, b, sigma):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned:
+            warnings.warn("admmnet_b200: forward is an inference fast path; the result is detached from autograd")
+            self._warned = True
+        src_dev = y.device
+        yd, bd, sd, _ = self._prep(y, b, sigma)
+        out = self.forward_device(yd, bd, sd)
+        return out if src_dev.type == "cuda" else out.to(src_dev)
+
+
+class ADMMNet(PhiEstADMMNet):
+    """admm_net.py:767-816 minus the learned PeakSearchLayer head (not built yet):
+    the unrolled loop is shared with PhiEstADMMNet; use utils.peakSearchUtils.alt_peak_search on phi."""
+
+    def forward(self, y, b, sigma):
+        raise NotImplementedError(
+            "ADMMNet's learned PeakSearchLayer head (admm_net.py:494-720) is outside this round's hot path; "
+            "use PhiEstADMMNet + alt_peak_search (main_for_net.py:99-117)")

@@ -1,0 +1,327 @@
+// extern "C" boundary (include/admmnet_b200.h): argument checks, workspace carving, launches.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/admmnet_b200.h"
+#include "net_kernels.cu"
+#include "classic_kernels.cu"
+#include "peak_kernels.cu"
+
+using namespace admmnet;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ADMMNET_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+extern "C" const char* admmnet_last_error(void) { return g_err.c_str(); }
+extern "C" int admmnet_version(void) { return 100; }
+extern "C" int admmnet_param_stride(int n) { return param_stride(n); }
+
+// ------------------------------------------------------------------------------------ workspace
+namespace {
+struct Ws {
+    float2 *Zp, *GV, *rot, *tau, *phi_cur;
+    float *Zr, *lam, *dT, *eT, *h_cur, *r, *mean;
+    int *nrot, *status;
+    double* rsum;
+    size_t bytes;
+};
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int default_rcap(int d) { return ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
+
+// n = signal length (for phi/h), d = matrix order.  Per-signal STATE arrays (Zp, GV, phi_cur, h_cur, r) cover
+// the whole batch B; the eigen-solver SCRATCH (Zr, rot, tau, lam, dT, eT, nrot) covers one chunk C <= B.
+Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
+    Ws w;
+    unsigned char* p = reinterpret_cast<unsigned char*>(base);
+    size_t off = 0;
+    const size_t npk = (size_t)d * (d + 1) / 2;
+    auto take = [&](size_t nbytes) { unsigned char* q = p + off; off += al(nbytes); return q; };
+    w.Zp = (float2*)take(B * npk * sizeof(float2));
+    w.GV = (float2*)take(B * npk * sizeof(float2));
+    w.Zr = (float*)take((size_t)C * d * d * sizeof(float));
+    w.rot = (float2*)take((size_t)C * rcap * sizeof(float2));
+    w.tau = (float2*)take((size_t)C * d * sizeof(float2));
+    w.lam = (float*)take((size_t)C * d * sizeof(float));
+    w.dT = (float*)take((size_t)C * d * sizeof(float));
+    w.eT = (float*)take((size_t)C * d * sizeof(float));
+    w.phi_cur = (float2*)take((size_t)B * n * sizeof(float2));
+    w.h_cur = (float*)take((size_t)B * n * sizeof(float));
+    w.r = (float*)take((size_t)B * sizeof(float));
+    w.nrot = (int*)take((size_t)C * sizeof(int));
+    w.rsum = (double*)take((size_t)(K + 1) * sizeof(double));
+    w.mean = (float*)take((size_t)(K + 1) * sizeof(float));
+    w.status = (int*)take(sizeof(int));
+    w.bytes = off;
+    return w;
+}
+
+int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
+    if (B <= 0 || K <= 0) return fail(ADMMNET_ERR_ARG, "B and K must be positive");
+    if (chunk <= 0 || chunk > B) chunk = B;
+    if (n < 2 || n > 127) return fail(ADMMNET_ERR_ARG, "n = M*N must be in [2,127] (matrix order d = n+1 <= 128)");
+    if (rcap == 0) rcap = default_rcap(n + 1);
+    if (rcap < 2048 || rcap % ROT_CHUNK) return fail(ADMMNET_ERR_ARG, "rcap must be a multiple of 1024, >= 2048");
+    return 0;
+}
+
+// the three eigen-solver launches after the tridiagonal form is in the workspace
+int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk, int with_c, float2* U_out,
+                    float* lamp_out, int* status, cudaStream_t st) {
+    {
+        const size_t sm = (size_t)2 * d * QL_THREADS * sizeof(double);
+        CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
+                                                                         status);
+        CK(cudaGetLastError());
+    }
+    {
+        const size_t sm = (size_t)2 * ROT_CHUNK * sizeof(float2) + (size_t)d * (d | 1) * sizeof(float);
+        CK(cudaFuncSetAttribute(k_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr);
+        CK(cudaGetLastError());
+    }
+    {
+        TailArgs t;
+        t.Zr = w.Zr; t.GV = w.GV; t.tau = w.tau; t.lam = w.lam; t.phi_cur = w.phi_cur; t.h_cur = w.h_cur;
+        t.Pk = Pk; t.r_out = w.r; t.U_out = U_out; t.lamp_out = lamp_out;
+        t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c;
+        const size_t sm = tail_smem_bytes(d, t.ldu);
+        if (d <= 104) {
+            CK(cudaFuncSetAttribute(k_tail<13, 416>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_tail<13, 416><<<B, 416, sm, st>>>(t);
+        } else {
+            CK(cudaFuncSetAttribute(k_tail<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_tail<16, 512><<<B, 512, sm, st>>>(t);
+        }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+}  // namespace
+
+// view of the workspace for the chunk [off, off+Bc): state pointers advanced, scratch untouched
+static Ws chunk_view(const Ws& w, int off, int n, int d) {
+    Ws c = w;
+    const size_t npk = (size_t)d * (d + 1) / 2;
+    c.Zp += (size_t)off * npk;
+    c.GV += (size_t)off * npk;
+    c.phi_cur += (size_t)off * n;
+    c.h_cur += (size_t)off * n;
+    c.r += off;
+    return c;
+}
+
+extern "C" int admmnet_forward_workspace_bytes(int B, int chunk, int n, int K, int rcap, size_t* bytes) {
+    if (!bytes) return fail(ADMMNET_ERR_ARG, "bytes is NULL");
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    *bytes = carve(nullptr, B, chunk, n, n + 1, K, rcap).bytes;
+    return 0;
+}
+
+extern "C" int admmnet_ws_scalars(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, double** rsum,
+                                  float** mean, int** status) {
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    if (rsum) *rsum = w.rsum;
+    if (mean) *mean = w.mean;
+    if (status) *status = w.status;
+    return 0;
+}
+
+extern "C" int admmnet_layer_chunk(const void* y, const void* b, const float* sigma, int B, int chunk, int sig_off,
+                                   int Bc, int Mdim, int Ndim, int K, int k, const float* params, void* ws,
+                                   size_t ws_bytes, int rcap, void* stream) {
+    const int n = Mdim * Ndim, d = n + 1;
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    if (!y || !b || !sigma || !params) return fail(ADMMNET_ERR_ARG, "null input pointer");
+    if (k < 0 || k >= K - 1) return fail(ADMMNET_ERR_ARG, "admmnet_layer_chunk: k must be in [0, K-2]");
+    if (sig_off < 0 || Bc <= 0 || Bc > chunk || sig_off + Bc > B) return fail(ADMMNET_ERR_ARG, "bad chunk range");
+    Ws wf = carve(ws, B, chunk, n, d, K, rcap);
+    if (!ws || ws_bytes < wf.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    Ws w = chunk_view(wf, sig_off, n, d);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ps = param_stride(n);
+    if (k == 0 && sig_off == 0) CK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
+    HeadArgs h;
+    h.y = (const float2*)y + (size_t)sig_off * n; h.b = (const float2*)b + (size_t)sig_off * n; h.sigma = sigma + sig_off;
+    h.Zp = w.Zp; h.GV = w.GV; h.phi_cur = w.phi_cur; h.h_cur = w.h_cur; h.r_prev = w.r;
+    h.mean_prev = k > 0 ? w.mean + (k - 1) : w.mean;
+    h.Pk = params + (size_t)k * ps; h.Pkm1 = k > 0 ? params + (size_t)(k - 1) * ps : params;
+    h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
+    h.B = Bc; h.n = n; h.d = d; h.ld = d | 1; h.first = (k == 0);
+    const size_t sm = head_smem_bytes(d, h.ld);
+    CK(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_head<<<Bc, 256, sm, st>>>(h);
+    CK(cudaGetLastError());
+    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st);
+}
+
+extern "C" int admmnet_layer_rsum(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k,
+                                  void* stream) {
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    if (k < 0 || k >= K) return fail(ADMMNET_ERR_ARG, "k out of range");
+    Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    k_rsum<<<1, 1024, 0, (cudaStream_t)stream>>>(w.r, B, w.rsum + k);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int admmnet_set_mean(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k,
+                                double count, void* stream) {
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    if (k < 0 || k >= K) return fail(ADMMNET_ERR_ARG, "k out of range");
+    Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    k_mean_from_sum<<<1, 32, 0, (cudaStream_t)stream>>>(w.rsum + k, count, w.mean + k);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int admmnet_final_phi(const void* y, const void* b, int B, int chunk, int Mdim, int Ndim, int K,
+                                 const float* params, void* phi_out, void* ws, size_t ws_bytes, int rcap, void* stream) {
+    const int n = Mdim * Ndim, d = n + 1;
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    if (!y || !b || !params || !phi_out) return fail(ADMMNET_ERR_ARG, "null pointer");
+    Ws w = carve(ws, B, chunk, n, d, K, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    const int ps = param_stride(n);
+    FinalArgs f;
+    f.y = (const float2*)y; f.b = (const float2*)b; f.Zp = w.Zp; f.GV = w.GV; f.phi_prev = w.phi_cur;
+    f.r_prev = w.r; f.mean_prev = K > 1 ? w.mean + (K - 2) : w.mean;
+    f.Pk = params + (size_t)(K - 1) * ps; f.Pkm1 = K > 1 ? params + (size_t)(K - 2) * ps : params;
+    f.phi_out = (float2*)phi_out; f.B = B; f.n = n; f.d = d; f.first = (K == 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 1) CK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
+    const long long nthreads = (long long)B * 32;
+    k_final_phi<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(f);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int admmnet_forward(const void* y, const void* b, const float* sigma, int B, int chunk, int Mdim, int Ndim,
+                               int K, const float* params, void* phi_out, void* ws, size_t ws_bytes, int rcap,
+                               void* stream) {
+    const int n = Mdim * Ndim;
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    for (int k = 0; k < K - 1; ++k) {
+        for (int off = 0; off < B; off += chunk) {
+            const int Bc = B - off < chunk ? B - off : chunk;
+            if (int e = admmnet_layer_chunk(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
+                                            stream))
+                return e;
+        }
+        if (int e = admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, stream)) return e;
+        if (int e = admmnet_set_mean(ws, ws_bytes, B, chunk, n, K, rcap, k, (double)B, stream)) return e;
+    }
+    return admmnet_final_phi(y, b, B, chunk, Mdim, Ndim, K, params, phi_out, ws, ws_bytes, rcap, stream);
+}
+
+extern "C" int admmnet_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream,
+                              int* status_host) {
+    if (!status_host) return fail(ADMMNET_ERR_ARG, "status_host is NULL");
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    CK(cudaMemcpyAsync(status_host, w.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ eigh taps
+extern "C" int admmnet_eigh_workspace_bytes(int B, int d, int rcap, size_t* bytes) {
+    if (!bytes) return fail(ADMMNET_ERR_ARG, "bytes is NULL");
+    if (B <= 0 || d < 3 || d > 128) return fail(ADMMNET_ERR_ARG, "need B > 0 and 3 <= d <= 128");
+    if (rcap == 0) rcap = default_rcap(d);
+    *bytes = carve(nullptr, B, B, d - 1, d, 1, rcap).bytes;
+    return 0;
+}
+
+extern "C" int admmnet_eigh_batched(const void* A, int B, int d, float* evals, void* evecs, void* fn_out,
+                                    const float* params, void* ws, size_t ws_bytes, int rcap, void* stream,
+                                    int* status_dev) {
+    if (B <= 0 || d < 3 || d > 128) return fail(ADMMNET_ERR_ARG, "need B > 0 and 3 <= d <= 128");
+    if (!A || !status_dev) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (rcap == 0) rcap = default_rcap(d);
+    if (rcap < 2048 || rcap % ROT_CHUNK) return fail(ADMMNET_ERR_ARG, "rcap must be a multiple of 1024, >= 2048");
+    Ws w = carve(ws, B, B, d - 1, d, 1, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ld = d | 1;
+    const size_t sm = head_smem_bytes(d, ld);
+    CK(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_tridiag<<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT);
+    CK(cudaGetLastError());
+    if (int e = launch_eig_tail(w, B, d - 1, d, rcap, params, params ? 0 : -1, (float2*)evecs, nullptr, status_dev, st))
+        return e;
+    const size_t npk = (size_t)d * (d + 1) / 2;
+    if (evals) CK(cudaMemcpyAsync(evals, w.lam, (size_t)B * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (fn_out) CK(cudaMemcpyAsync(fn_out, w.GV, (size_t)B * npk * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ classical ADMM
+extern "C" int admm_classic_forward(const void* y, const void* b, int in_is_c128, int B, int n, double rho, int n_iter,
+                                    void* phi_out, void* stream) {
+    if (!y || !b || !phi_out) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (B <= 0 || n <= 0 || n > 256 || n_iter < 0) return fail(ADMMNET_ERR_ARG, "need B > 0, 0 < n <= 256, n_iter >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (B * 32 + 255) / 256;
+    if (n <= 128) {
+        if (in_is_c128) k_classic<double2, 4><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        else k_classic<float2, 4><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
+    } else {
+        if (in_is_c128) k_classic<double2, 8><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        else k_classic<float2, 8><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ peak search
+extern "C" int peak_search_full(const void* phi, int phi_is_c128, int B, int xbase, int ybase, const double* axis_x,
+                                int Gx, const double* axis_y, int Gy, double xmin, double xmax, double xstep,
+                                double ymin, double ymax, double ystep, double reducefactor, int iters, int pmax,
+                                double* peaks, int* count, int topl, double* top, double* surface, int* status_dev,
+                                void* stream) {
+    if (!phi || !axis_x || !axis_y || !peaks || !count || !status_dev) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (B <= 0 || Gx <= 0 || Gy <= 0 || pmax <= 0 || iters < 0 || topl < 0) return fail(ADMMNET_ERR_ARG, "bad sizes");
+    if (xbase < 1 || ybase < 1 || xbase > PEAK_MAX_BASE || ybase > PEAK_MAX_BASE)
+        return fail(ADMMNET_ERR_ARG, "xbase/ybase must be in [1,32]");
+    if (topl > 0 && !top) return fail(ADMMNET_ERR_ARG, "top is NULL");
+    const size_t sm = peak_smem_bytes(Gx, Gy, xbase, ybase, pmax);
+    if (sm > 227 * 1024) return fail(ADMMNET_ERR_ARG, "coarse grid too large for one CTA's shared memory");
+    PeakArgs a;
+    a.phi = phi; a.phi_is_c128 = phi_is_c128; a.B = B; a.xb = xbase; a.yb = ybase;
+    a.axis_x = axis_x; a.axis_y = axis_y; a.Gx = Gx; a.Gy = Gy;
+    a.xmin = xmin; a.xmax = xmax; a.xstep = xstep; a.ymin = ymin; a.ymax = ymax; a.ystep = ystep;
+    a.reducefactor = reducefactor; a.iters = iters; a.pmax = pmax; a.peaks = peaks; a.count = count;
+    a.topl = topl; a.top = top; a.surface = surface; a.status = status_dev;
+    CK(cudaFuncSetAttribute(k_peak_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_peak_search<<<B, 256, sm, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int peak_search_points(const void* phi, int phi_is_c128, int xbase, int ybase, const double* X,
+                                  const double* Y, int npts, double* out, void* stream) {
+    if (!phi || !X || !Y || !out) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (npts <= 0) return 0;
+    if (xbase < 1 || ybase < 1 || xbase > PEAK_MAX_BASE || ybase > PEAK_MAX_BASE)
+        return fail(ADMMNET_ERR_ARG, "xbase/ybase must be in [1,32]");
+    const size_t sm = (size_t)xbase * ybase * sizeof(double2);
+    k_peak_points<<<(npts + 255) / 256, 256, sm, (cudaStream_t)stream>>>(phi, phi_is_c128, xbase, ybase, X, Y, npts, out);
+    CK(cudaGetLastError());
+    return 0;
+}

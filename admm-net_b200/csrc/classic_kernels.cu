@@ -1,0 +1,78 @@
+// Classical ADMM (reference admm.py:6-114) as evaluated for every reachable input (SURVEY.md §8a-9,
+// App. A.3; oracle/classic_oracle.py::admm_linear_recursion):
+//     M = diag(1/|b|^2) + rho 1 1^T ,  phi_0 = 0 ,  phi_k = M^{-1} (y/b + rho phi_{k-1})
+// with M^{-1} v = D v - rho D 1 (1^T D v) / (1 + rho 1^T D 1),  D = diag(|b|^2)  (Sherman-Morrison).
+// fp64 / complex128 like the reference.  One warp per signal; the kernel is HBM-bound
+// (reads y,b, writes phi: 3 * 16 B * n per signal for complex128 I/O).
+#include "common.cuh"
+
+namespace admmnet {
+
+template <typename CIn>
+__device__ __forceinline__ double2 ld_c(const CIn* p, size_t i);
+template <>
+__device__ __forceinline__ double2 ld_c<double2>(const double2* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ double2 ld_c<float2>(const float2* p, size_t i) {
+    const float2 v = p[i];
+    return make_double2((double)v.x, (double)v.y);
+}
+
+// MAXE: elements per lane (n <= 32*MAXE)
+template <typename CIn, int MAXE>
+__global__ void __launch_bounds__(256)
+k_classic(const CIn* __restrict__ y, const CIn* __restrict__ b, int B, int n, double rho, int n_iter,
+          double2* __restrict__ phi_out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= B) return;
+    double D[MAXE];
+    double2 yb[MAXE], phi[MAXE];
+    double dsum = 0.0;
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        const int j = lane + 32 * e;
+        D[e] = 0.0;
+        yb[e] = make_double2(0.0, 0.0);
+        phi[e] = make_double2(0.0, 0.0);
+        if (j < n) {
+            const double2 bj = ld_c<CIn>(b, (size_t)w * n + j), yj = ld_c<CIn>(y, (size_t)w * n + j);
+            D[e] = bj.x * bj.x + bj.y * bj.y;                 // (b * conj(b)).real          admm.py:78
+            const double den = D[e];
+            yb[e] = make_double2((yj.x * bj.x + yj.y * bj.y) / den, (yj.y * bj.x - yj.x * bj.y) / den);   // inv(diag(b)) @ y
+            dsum += D[e];
+        }
+    }
+    dsum = warp_sum(dsum);
+    const double den = 1.0 + rho * dsum;
+    for (int it = 0; it < n_iter; ++it) {
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            // v = y/b + rho*phi ; Dv = D*v
+            phi[e].x = D[e] * (yb[e].x + rho * phi[e].x);
+            phi[e].y = D[e] * (yb[e].y + rho * phi[e].y);
+            sx += phi[e].x;
+            sy += phi[e].y;
+        }
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        const double fx = rho * sx / den, fy = rho * sy / den;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            phi[e].x -= D[e] * fx;
+            phi[e].y -= D[e] * fy;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        const int j = lane + 32 * e;
+        if (j < n) phi_out[(size_t)w * n + j] = phi[e];
+    }
+}
+
+template __global__ void k_classic<double2, 4>(const double2*, const double2*, int, int, double, int, double2*);
+template __global__ void k_classic<float2, 4>(const float2*, const float2*, int, int, double, int, double2*);
+template __global__ void k_classic<double2, 8>(const double2*, const double2*, int, int, double, int, double2*);
+template __global__ void k_classic<float2, 8>(const float2*, const float2*, int, int, double, int, double2*);
+
+}  // namespace admmnet

@@ -1,0 +1,774 @@
+// ADMM-Net layer kernels for sm_100a.
+//
+// One unrolled layer (reference: admm_net.py:757-762) is five launches over a chunk of signals:
+//   k_head   : Z += alpha*(G-C) of the previous layer (ZLayer, admm_net.py:388-412), phi-update
+//              (PhiLayer, 79-105), H-update (HLayer, 134-194), build the Hermitian block matrix
+//              (GLayer._build_block_matrix, 262-290) in shared memory and reduce it to real
+//              tridiagonal form by Householder reflectors (first half of torch.linalg.eigh, 303).
+//   k_ql     : implicit-shift QL on the tridiagonal, one thread per signal, fp64 scalars; emits
+//              eigenvalues and the plane-rotation stream.
+//   k_rot    : applies the rotation stream to I (rows are independent) -> real eigenvectors of T.
+//   k_tail   : back-transforms with the reflectors (U = Q_H * Z), maps eigenvalues
+//              (GLayer._eigenvalues_projection, 310-334), rebuilds G = U diag(l') U^H (336-354)
+//              and the residual norm r = ||G - C||_F (ZLayer._compute_adaptive_step, 454).
+//   k_mean   : batch mean of r (admm_net.py:459), deterministic.
+// The last layer only needs the phi-update (k_final_phi): its H/G/Z updates never reach the output.
+#include "common.cuh"
+
+namespace admmnet {
+
+// =====================================================================================
+// Householder tridiagonalisation of a Hermitian matrix held in shared memory.
+//   A : column-major, leading dimension ld (odd), both triangles valid on entry.
+// On exit the strictly-lower part of column k (rows k+2..d-1) holds v_k (v_k[k+1] = 1 implicit),
+// tau[k] the reflector scalars, dd/ee the real tridiagonal.  A = Q T Q^H, Q = H_0 H_1 ... H_{d-2},
+// H_k = I - tau_k v_k v_k^H   (same convention as LAPACK zhetd2 'L').
+// 256 threads: (r = tid & 127, half = tid >> 7).
+// =====================================================================================
+struct TriScratch {
+    float2* v;      // [128]
+    float2* w;      // [128]
+    float2* part;   // [256]
+    float* red;     // [96]
+    float2* scal;   // [4]: tau, scale, (beta,0)
+};
+
+__device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S, float2* tau_out, float* dd,
+                             float* ee) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r = tid & 127, half = tid >> 7;
+    for (int k = 0; k < d - 1; ++k) {
+        const int m = d - k - 1;            // trailing size, rows/cols k+1..d-1
+        float2* colk = A + (size_t)k * ld;  // column k
+        // ---- S1: reflector scalars (warp 0)
+        if (wid == 0) {
+            float ss = 0.f;
+            for (int i = k + 2 + lane; i < d; i += 32) {
+                float2 x = colk[i];
+                ss += x.x * x.x + x.y * x.y;
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) {
+                const float2 alpha = colk[k + 1];
+                float2 tau, scale;
+                float beta;
+                if (ss == 0.f && alpha.y == 0.f) {
+                    tau = make_float2(0.f, 0.f);
+                    scale = make_float2(0.f, 0.f);
+                    beta = alpha.x;
+                } else {
+                    beta = -copysignf(sqrtf(alpha.x * alpha.x + alpha.y * alpha.y + ss), alpha.x);
+                    tau = make_float2((beta - alpha.x) / beta, -alpha.y / beta);
+                    scale = cdiv(make_float2(1.f, 0.f), make_float2(alpha.x - beta, alpha.y));
+                }
+                S.scal[0] = tau;
+                S.scal[1] = scale;
+                tau_out[k] = tau;
+                ee[k] = beta;
+                dd[k] = A[k + (size_t)k * ld].x;
+            }
+        }
+        __syncthreads();
+        const float2 tau = S.scal[0];
+        if (tau.x != 0.f || tau.y != 0.f) {  // uniform branch (H_k == I otherwise)
+            const float2 scale = S.scal[1];
+            if (tid < m) {
+                float2 vi = make_float2(1.f, 0.f);
+                if (tid > 0) {
+                    vi = cmul(colk[k + 1 + tid], scale);
+                    colk[k + 1 + tid] = vi;
+                }
+                S.v[tid] = vi;
+            }
+            __syncthreads();
+            // ---- S2: p = A22 v (two interleaved column halves)
+            {
+                float2 acc = make_float2(0.f, 0.f);
+                if (r < m) {
+                    const float2* a = A + (k + 1 + r) + (size_t)(k + 1) * ld;
+#pragma unroll 4
+                    for (int c = half; c < m; c += 2) {
+                        const float2 x = a[(size_t)c * ld];
+                        const float2 vc = S.v[c];
+                        acc.x += x.x * vc.x - x.y * vc.y;
+                        acc.y += x.x * vc.y + x.y * vc.x;
+                    }
+                }
+                S.part[tid] = acc;
+            }
+            __syncthreads();
+            // ---- S3: p = tau*(..), dot = p^H v, w = p - (tau/2)(p^H v) v
+            float2 p = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
+            float dot[2] = {0.f, 0.f};
+            if (tid < m) {
+                p = cmul(tau, cadd(S.part[tid], S.part[tid + 128]));
+                vr = S.v[tid];
+                const float2 t = cconjmul(p, vr);
+                dot[0] = t.x;
+                dot[1] = t.y;
+            }
+            block_sum<2>(dot, S.red);
+            const float2 a2 = cmul(make_float2(-0.5f * tau.x, -0.5f * tau.y), make_float2(dot[0], dot[1]));
+            if (tid < m) S.w[tid] = cadd(p, cmul(a2, vr));
+            __syncthreads();
+            // ---- S4: A22 -= v w^H + w v^H
+            if (r < m) {
+                const float2 vrr = S.v[r], wrr = S.w[r];
+                float2* a = A + (k + 1 + r) + (size_t)(k + 1) * ld;
+#pragma unroll 4
+                for (int c = half; c < m; c += 2) {
+                    const float2 vc = S.v[c], wc = S.w[c];
+                    float2 x = a[(size_t)c * ld];
+                    // v_r conj(w_c) + w_r conj(v_c)
+                    x.x -= vrr.x * wc.x + vrr.y * wc.y + wrr.x * vc.x + wrr.y * vc.y;
+                    x.y -= vrr.y * wc.x - vrr.x * wc.y + wrr.y * vc.x - wrr.x * vc.y;
+                    a[(size_t)c * ld] = x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) dd[d - 1] = A[(d - 1) + (size_t)(d - 1) * ld].x;
+    __syncthreads();
+}
+
+// Export reflectors (column-concatenated), tau, and the tridiagonal ([i][B] layout for k_ql).
+__device__ void export_tridiag(const float2* __restrict__ A, int d, int ld, const float2* tau_s, const float* dd,
+                               const float* ee, float2* __restrict__ Vg, float2* __restrict__ taug,
+                               float* __restrict__ dT, float* __restrict__ eT, int B, int sig) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    for (int k = wid; k < d - 2; k += nw) {
+        const int off = voff(k, d);
+        for (int i = k + 2 + lane; i < d; i += 32) Vg[off + i - (k + 2)] = A[i + (size_t)k * ld];
+    }
+    for (int i = tid; i < d; i += blockDim.x) {
+        taug[i] = i < d - 1 ? tau_s[i] : make_float2(0.f, 0.f);
+        dT[(size_t)i * B + sig] = dd[i];
+        eT[(size_t)i * B + sig] = i < d - 1 ? ee[i] : 0.f;
+    }
+}
+
+// shared-memory carve-up shared by k_head and k_tridiag
+struct HeadSmem {
+    float2* A;
+    TriScratch S;
+    float2* tau;
+    float* dd;
+    float* ee;
+    float2* phi;    // [n]
+    float2* gcol;   // [n]
+    float2* zeta;   // [n]
+    float2* phip;   // [n] previous phi
+    float* hp;      // [n] previous h
+    float* t;       // [n]
+    float* hid;     // [64]
+    float* h;       // [n]
+};
+__host__ __device__ inline size_t head_smem_bytes(int d, int ld) {
+    size_t f2 = (size_t)d * ld + 128 + 128 + 256 + 4 + 128 /*tau*/ + 4 * 128 /*phi,gcol,zeta,phip*/;
+    size_t f1 = 96 + 128 + 128 /*dd,ee*/ + 128 /*hp*/ + 128 /*t*/ + 64 + 128 /*h*/;
+    return f2 * sizeof(float2) + f1 * sizeof(float);
+}
+__device__ inline HeadSmem carve_head(unsigned char* base, int d, int ld) {
+    HeadSmem s;
+    float2* p2 = reinterpret_cast<float2*>(base);
+    s.A = p2; p2 += (size_t)d * ld;
+    s.S.v = p2; p2 += 128;
+    s.S.w = p2; p2 += 128;
+    s.S.part = p2; p2 += 256;
+    s.S.scal = p2; p2 += 4;
+    s.tau = p2; p2 += 128;
+    s.phi = p2; p2 += 128;
+    s.gcol = p2; p2 += 128;
+    s.zeta = p2; p2 += 128;
+    s.phip = p2; p2 += 128;
+    float* p1 = reinterpret_cast<float*>(p2);
+    s.S.red = p1; p1 += 96;
+    s.dd = p1; p1 += 128;
+    s.ee = p1; p1 += 128;
+    s.hp = p1; p1 += 128;
+    s.t = p1; p1 += 128;
+    s.hid = p1; p1 += 64;
+    s.h = p1; p1 += 128;
+    return s;
+}
+
+struct HeadArgs {
+    const float2* y;
+    const float2* b;
+    const float* sigma;
+    float2* Zp;          // [B][npk]
+    float2* GV;          // [B][npk]: G (packed lower) of the previous layer on entry, reflectors on exit
+    float2* phi_cur;     // [B][n]
+    float* h_cur;        // [B][n]
+    const float* r_prev; // [B]
+    const float* mean_prev;
+    const float* Pk;
+    const float* Pkm1;
+    float2* tau;         // [B][d]
+    float* dT;           // [d][B]
+    float* eT;           // [d][B]
+    int B, n, d, ld, first;
+};
+
+__global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, d = a.d, ld = a.ld;
+    HeadSmem s = carve_head(smem_raw, d, ld);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int sig = blockIdx.x;
+    const int npk = d * (d + 1) / 2;
+    const float* __restrict__ P = a.Pk;
+    float2* Zp = a.Zp + (size_t)sig * npk;
+    float2* GV = a.GV + (size_t)sig * npk;
+    const float inv_rho_g = P[P_INV_RHO_G];
+    const float rho_h_eps = P[P_RHO_H_EPS];
+
+    // ---- stage previous phi/h, clear captures
+    for (int j = tid; j < n; j += 256) {
+        s.gcol[j] = make_float2(0.f, 0.f);
+        s.zeta[j] = make_float2(0.f, 0.f);
+        s.t[j] = 0.f;
+        if (!a.first) {
+            s.phip[j] = a.phi_cur[(size_t)sig * n + j];
+            s.hp[j] = a.h_cur[(size_t)sig * n + j];
+        }
+    }
+    __syncthreads();
+    // ---- dual update of the previous layer + A = -Z/(rho_g+eps)
+    if (a.first) {
+        for (int idx = tid; idx < d * ld; idx += 256) s.A[idx] = make_float2(0.f, 0.f);
+        for (int idx = tid; idx < npk; idx += 256) Zp[idx] = make_float2(0.f, 0.f);   // Z_0 = 0 (admm_net.py:754)
+    } else {
+        const float alpha = z_alpha(a.Pkm1, a.r_prev[sig], *a.mean_prev);
+        const float c1z = a.Pkm1[P_C1Z];
+        for (int i = wid; i < d; i += 8) {
+            for (int j = lane; j <= i; j += 32) {
+                const int idx = pk(i, j);
+                float2 z = Zp[idx];
+                const float2 g = GV[idx];
+                float2 c = make_float2(0.f, 0.f);
+                if (i == j) c.x = (i < n) ? s.hp[i] : c1z;
+                else if (i == n) c = cconj(s.phip[j]);
+                z.x += alpha * (g.x - c.x);
+                z.y += alpha * (g.y - c.y);
+                if (i == j) z.y = 0.f;
+                Zp[idx] = z;
+                if (i == j && i < n) s.t[i] = g.x + z.x / rho_h_eps;
+                if (i == n && j < n) {
+                    s.gcol[j] = cconj(g);
+                    s.zeta[j] = cconj(z);
+                }
+                const float2 av = make_float2(-inv_rho_g * z.x, -inv_rho_g * z.y);
+                s.A[i + (size_t)j * ld] = av;
+                if (i != j) s.A[j + (size_t)i * ld] = cconj(av);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phi update (admm_net.py:94-103)
+    const float rho_phi = P[P_RHO_PHI];
+    for (int j = tid; j < n; j += 256) {
+        const float2 bj = a.b[(size_t)sig * n + j], yj = a.y[(size_t)sig * n + j];
+        const float ab = hypotf(bj.x, bj.y);
+        const float bsq = ab * ab + ADMM_EPS;
+        const float wgt = bsq / (1.f + rho_phi * bsq);
+        const float2 yob = cdiv(yj, make_float2(bj.x + ADMM_EPS, bj.y));
+        const float2 g = s.gcol[j], z = s.zeta[j];
+        const float2 ph = make_float2(wgt * (yob.x + rho_phi * g.x + z.x), wgt * (yob.y + rho_phi * g.y + z.y));
+        s.phi[j] = ph;
+        a.phi_cur[(size_t)sig * n + j] = ph;
+    }
+    // ---- H update (admm_net.py:146-192): correction MLP n -> 64 -> n
+    if (tid < 64) {
+        float acc = P[P_HB1 + tid];
+        const float* __restrict__ W1T = P + P_HW1T;
+        for (int i = 0; i < n; ++i) acc += W1T[i * 64 + tid] * s.t[i];
+        s.hid[tid] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    float tc = 0.f;
+    if (tid < n) {
+        const float* __restrict__ W2T = P + P_HW1T + 64 * n;
+        float acc = P[P_HW1T + 128 * n + tid];
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) acc += W2T[j * n + tid] * s.hid[j];
+        tc = s.t[tid] + 0.1f * tanhf(acc);
+    }
+    {
+        const float linf = block_max(tid < n ? fabsf(tc) : 0.f, s.S.red);
+        float sm[1] = {tid < n ? tc : 0.f};
+        block_sum<1>(sm, s.S.red);
+        const float sg = a.sigma[sig];
+        const float Asig = 2.f * sqrtf((float)n) * sg + sg * sg;
+        const float cv = Asig * linf + sm[0];
+        const float scale = fminf(P[P_SIG_PW] / (cv + ADMM_EPS), 1.f);
+        if (tid < n) {
+            const float hv = tc * scale;
+            s.h[tid] = hv;
+            a.h_cur[(size_t)sig * n + tid] = hv;
+        }
+    }
+    __syncthreads();
+    // ---- A += [[diag(h), phi],[phi^H, c0]]
+    for (int j = tid; j < n; j += 256) {
+        s.A[j + (size_t)j * ld].x += s.h[j];
+        const float2 ph = s.phi[j];
+        float2* up = &s.A[j + (size_t)n * ld];   // A[j][n]
+        up->x += ph.x; up->y += ph.y;
+        float2* lo = &s.A[n + (size_t)j * ld];   // A[n][j]
+        lo->x += ph.x; lo->y -= ph.y;
+    }
+    if (tid == 0) s.A[n + (size_t)n * ld].x += P[P_C0];
+    __syncthreads();
+    // ---- eigh, stage 1
+    tridiag_smem(s.A, d, ld, s.S, s.tau, s.dd, s.ee);
+    export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, GV, a.tau + (size_t)sig * d, a.dT, a.eT, a.B, sig);
+}
+
+// Debug/unit entry: tridiagonalise arbitrary Hermitian matrices given as full row-major [B][d][d]
+// (lower triangle is read).
+__global__ void __launch_bounds__(256, 2)
+k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, float2* tau, float* dT, float* eT) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HeadSmem s = carve_head(smem_raw, d, ld);
+    const int sig = blockIdx.x;
+    const int npk = d * (d + 1) / 2;
+    const float2* Ag = Afull + (size_t)sig * d * d;
+    for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
+        const int i = idx / d, j = idx % d;
+        if (j <= i) {
+            float2 v = Ag[idx];
+            if (i == j) v.y = 0.f;
+            s.A[i + (size_t)j * ld] = v;
+            if (i != j) s.A[j + (size_t)i * ld] = cconj(v);
+        }
+    }
+    __syncthreads();
+    tridiag_smem(s.A, d, ld, s.S, s.tau, s.dd, s.ee);
+    export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, V + (size_t)sig * npk, tau + (size_t)sig * d, dT, eT, B, sig);
+}
+
+// =====================================================================================
+// k_ql: implicit QL with Wilkinson shift on the real symmetric tridiagonal, one thread per signal.
+// Scalars in fp64 (the rotation parameters decide the accuracy of f(A));
+// rotations are emitted as fp32 (c,s).
+// Stream format per signal (float2 entries): [header (m, cnt as int bits)] [cnt x (c,s)] ... [header m=-1].
+// A sweep starting at m applies rotations to column pairs (i,i+1), i = m-1, m-2, ..., m-cnt.
+// =====================================================================================
+#define QL_THREADS 64
+#define QL_MAXIT 60
+
+__global__ void __launch_bounds__(QL_THREADS)
+k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, float* __restrict__ lam,
+     float2* __restrict__ rot, int rcap, int* __restrict__ nrot, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sd = reinterpret_cast<double*>(smem_raw);
+    double* se = sd + (size_t)d * QL_THREADS;
+    const int t = threadIdx.x;
+    const int sig = blockIdx.x * QL_THREADS + t;
+    if (sig >= B) return;
+#define D_(i) sd[(i) * QL_THREADS + t]
+#define E_(i) se[(i) * QL_THREADS + t]
+    double anorm = 0.0;
+    for (int i = 0; i < d; ++i) {
+        const double di = dT[(size_t)i * B + sig], ei = eT[(size_t)i * B + sig];
+        D_(i) = di;
+        E_(i) = ei;
+        anorm = fmax(anorm, fmax(fabs(di), fabs(ei)));
+    }
+    const double eps = 3.0e-8, floor_abs = 1.0e-9 * anorm;
+    float2* out = rot + (size_t)sig * rcap;
+    int nrec = 0;
+    bool fail = false;
+    for (int l = 0; l < d && !fail; ++l) {
+        int iter = 0;
+        while (true) {
+            int m = l;
+            for (; m < d - 1; ++m) {
+                const double ddm = fabs(D_(m)) + fabs(D_(m + 1));
+                if (fabs(E_(m)) <= eps * ddm + floor_abs) break;
+            }
+            if (m == l) break;
+            if (iter++ == QL_MAXIT) { fail = true; break; }
+            double g = (D_(l + 1) - D_(l)) / (2.0 * E_(l));
+            double r = sqrt(g * g + 1.0);
+            g = D_(m) - D_(l) + E_(l) / (g + copysign(r, g));
+            double s = 1.0, c = 1.0, p = 0.0;
+            const int hdr = nrec++;
+            int cnt = 0;
+            bool early = false;
+            for (int i = m - 1; i >= l; --i) {
+                const double f = s * E_(i), bb = c * E_(i);
+                r = sqrt(f * f + g * g);
+                E_(i + 1) = r;
+                if (r == 0.0) {
+                    D_(i + 1) -= p;
+                    E_(m) = 0.0;
+                    early = true;
+                    break;
+                }
+                s = f / r;
+                c = g / r;
+                g = D_(i + 1) - p;
+                r = (D_(i) - g) * s + 2.0 * c * bb;
+                p = s * r;
+                D_(i + 1) = g + p;
+                g = c * r - bb;
+                if (nrec < rcap - 1) out[nrec] = make_float2((float)c, (float)s);
+                ++nrec;
+                ++cnt;
+            }
+            if (!early) {
+                D_(l) -= p;
+                E_(l) = g;
+                E_(m) = 0.0;
+            }
+            if (hdr < rcap - 1) out[hdr] = make_float2(__int_as_float(m), __int_as_float(cnt));
+            if (nrec >= rcap - 1) { fail = true; break; }
+        }
+    }
+    if (fail) {
+        atomicOr(status, 1);
+        nrec = 0;   // consumer leaves Z = I; the status word is the error report
+    }
+    out[nrec] = make_float2(__int_as_float(-1), __int_as_float(0));
+    nrot[sig] = nrec + 1;
+    for (int i = 0; i < d; ++i) lam[(size_t)sig * d + i] = (float)D_(i);
+#undef D_
+#undef E_
+}
+
+// =====================================================================================
+// k_rot: Z = I * (product of the recorded plane rotations).  One CTA per signal, thread = row of Z.
+// The rotation stream is staged through shared memory in double-buffered cp.async chunks.
+// =====================================================================================
+#define ROT_THREADS 128
+#define ROT_CHUNK 1024   // float2 entries per stage (8 KB)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(ROT_THREADS)
+k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* stage = reinterpret_cast<float2*>(smem_raw);                  // [2][ROT_CHUNK]
+    float* z = reinterpret_cast<float*>(stage + 2 * ROT_CHUNK);           // [d][ldz]
+    const int ldz = d | 1;
+    const int tid = threadIdx.x;
+    const int sig = blockIdx.x;
+    const float2* src = rot + (size_t)sig * rcap;
+    const int total = nrot[sig];
+    for (int idx = tid; idx < d * ldz; idx += ROT_THREADS) z[idx] = 0.f;
+    __syncthreads();
+    if (tid < d) z[tid * ldz + tid] = 1.f;
+    const int nchunks = (total + ROT_CHUNK - 1) / ROT_CHUNK;
+    auto issue = [&](int ch) {
+        const float2* g = src + (size_t)ch * ROT_CHUNK;
+        float2* sdst = stage + (ch & 1) * ROT_CHUNK;
+        // whole chunks are always readable: rcap is a multiple of ROT_CHUNK (checked on the host)
+        for (int q = tid; q < ROT_CHUNK / 2; q += ROT_THREADS) cp_async16(sdst + 2 * q, g + 2 * q);
+        cp_async_commit();
+    };
+    if (nchunks > 0) issue(0);
+    // parser state (identical in every thread; rows differ only in data)
+    int remaining = 0, col = 0;
+    float carry = 0.f;
+    bool done = false;
+    float* zr = z + (size_t)tid * ldz;
+    const bool active = tid < d;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) { issue(ch + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const float2* sbuf = stage + (ch & 1) * ROT_CHUNK;
+        const int cnt_here = min(ROT_CHUNK, total - ch * ROT_CHUNK);
+        if (!done) {
+            for (int q = 0; q < cnt_here; ++q) {
+                const float2 e = sbuf[q];
+                if (remaining == 0) {
+                    const int m = __float_as_int(e.x);
+                    if (m < 0) { done = true; break; }
+                    remaining = __float_as_int(e.y);
+                    col = m;                       // carry holds z[col]
+                    if (active) carry = zr[col];
+                    if (remaining == 0 && active) zr[col] = carry;
+                } else {
+                    if (active) {
+                        const float zi = zr[col - 1];
+                        zr[col] = e.y * zi + e.x * carry;     // z[i+1] = s*z[i] + c*f
+                        carry = e.x * zi - e.y * carry;       // z[i]   = c*z[i] - s*f
+                    }
+                    --col;
+                    if (--remaining == 0 && active) zr[col] = carry;
+                }
+            }
+        }
+        __syncthreads();   // stage buffer (ch&1) is refilled by issue(ch+2)
+    }
+    __syncthreads();
+    float* outz = Zr + (size_t)sig * d * d;
+    for (int idx = tid; idx < d * d; idx += ROT_THREADS) outz[idx] = z[(idx / d) * ldz + (idx % d)];
+}
+
+// =====================================================================================
+// k_tail: U = Q_H Z, l' = f(l), G = U diag(l') U^H (lower triangle), r = ||G - C||_F.
+// Thread mapping for the back-transformation: (column pair cp = tid>>3, row split s = tid&7),
+// rows s+8j kept in registers for all d-1 reflectors -> no block barrier inside that phase.
+// =====================================================================================
+struct TailArgs {
+    const float* Zr;        // [B][d][d]
+    float2* GV;             // [B][npk]: reflectors on entry, G packed lower on exit
+    const float2* tau;      // [B][d]
+    const float* lam;       // [B][d]
+    const float2* phi_cur;  // [B][n]
+    const float* h_cur;     // [B][n]
+    const float* Pk;
+    float* r_out;           // [B]
+    float2* U_out;          // optional [B][d][d] row-major eigenvectors (debug taps), may be null
+    float* lamp_out;        // optional [B][d]
+    int B, n, d, ldu, with_c;  // with_c=0: plain f(A) for the debug entry (no residual)
+};
+__host__ __device__ inline size_t tail_smem_bytes(int d, int ldu) {
+    const size_t nv = (size_t)(d - 1) * (d - 2) / 2;
+    return ((size_t)d * ldu + nv + 2 + 128 /*tau*/ + 128 /*phi*/) * sizeof(float2) + (128 + 128 + 96) * sizeof(float);
+}
+
+template <int NR, int NT>
+__global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, d = a.d, ldu = a.ldu;
+    const int nv = (d - 1) * (d - 2) / 2;
+    float2* U = reinterpret_cast<float2*>(smem_raw);          // [d][ldu] column-major (also Z staging)
+    float2* Vs = U + (size_t)d * ldu;                         // reflectors
+    float2* taus = Vs + ((nv + 1) & ~1);
+    float2* phis = taus + 128;
+    float* lamp = reinterpret_cast<float*>(phis + 128);       // [128] mapped eigenvalues
+    float* hs = lamp + 128;
+    float* red = hs + 128;
+    const int tid = threadIdx.x;
+    const int sig = blockIdx.x;
+    const int npk = d * (d + 1) / 2;
+    float2* GV = a.GV + (size_t)sig * npk;
+    const float* __restrict__ P = a.Pk;
+
+    // ---- phase A: stage reflectors, Z, per-signal vectors
+    for (int idx = tid; idx < nv; idx += NT) Vs[idx] = GV[idx];
+    float* Zs = reinterpret_cast<float*>(U);
+    const float* Zg = a.Zr + (size_t)sig * d * d;
+    for (int idx = tid; idx < d * d; idx += NT) Zs[idx] = Zg[idx];
+    for (int i = tid; i < d; i += NT) {
+        taus[i] = a.tau[(size_t)sig * d + i];
+        const float l = a.lam[(size_t)sig * d + i];
+        const float lp = a.with_c >= 0 ? eig_map(P, l) : l;
+        lamp[i] = lp;
+        if (a.lamp_out) a.lamp_out[(size_t)sig * d + i] = lp;
+    }
+    if (a.with_c > 0) {
+        for (int j = tid; j < n; j += NT) {
+            phis[j] = a.phi_cur[(size_t)sig * n + j];
+            hs[j] = a.h_cur[(size_t)sig * n + j];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: back-transformation in registers
+    const int s8 = tid & 7, cp = tid >> 3;
+    const int c0 = 2 * cp, c1 = 2 * cp + 1;
+    float2 M0[NR], M1[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const int r = s8 + 8 * j;
+        M0[j] = make_float2((r < d && c0 < d) ? Zs[r * d + c0] : 0.f, 0.f);
+        M1[j] = make_float2((r < d && c1 < d) ? Zs[r * d + c1] : 0.f, 0.f);
+    }
+    __syncthreads();   // Z staging area is dead from here on (becomes U)
+    for (int k = d - 2; k >= 0; --k) {
+        const float2 tk = taus[k];
+        if (tk.x == 0.f && tk.y == 0.f) continue;
+        const float2* vk = Vs + voff(k, d) - (k + 2);     // vk[r] valid for r >= k+2
+        float2 vv[NR];
+        float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            vv[j] = make_float2(0.f, 0.f);
+            if (8 * j + 7 >= k + 1) {
+                const int r = s8 + 8 * j;
+                if (r > k && r < d) {
+                    const float2 v = (r == k + 1) ? make_float2(1.f, 0.f) : vk[r];
+                    vv[j] = v;
+                    d0.x += v.x * M0[j].x + v.y * M0[j].y;
+                    d0.y += v.x * M0[j].y - v.y * M0[j].x;
+                    d1.x += v.x * M1[j].x + v.y * M1[j].y;
+                    d1.y += v.x * M1[j].y - v.y * M1[j].x;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            d0.x += __shfl_xor_sync(0xffffffffu, d0.x, o);
+            d0.y += __shfl_xor_sync(0xffffffffu, d0.y, o);
+            d1.x += __shfl_xor_sync(0xffffffffu, d1.x, o);
+            d1.y += __shfl_xor_sync(0xffffffffu, d1.y, o);
+        }
+        const float2 t0 = cmul(tk, d0), t1 = cmul(tk, d1);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            if (8 * j + 7 >= k + 1) {
+                const float2 v = vv[j];
+                M0[j].x -= t0.x * v.x - t0.y * v.y;
+                M0[j].y -= t0.x * v.y + t0.y * v.x;
+                M1[j].x -= t1.x * v.x - t1.y * v.y;
+                M1[j].y -= t1.x * v.y + t1.y * v.x;
+            }
+        }
+    }
+    // ---- phase C: U to shared memory (column-major, zero padded rows) and optional global tap
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const int r = s8 + 8 * j;
+        if (r < ldu) {
+            if (c0 < d) U[(size_t)c0 * ldu + r] = r < d ? M0[j] : make_float2(0.f, 0.f);
+            if (c1 < d) U[(size_t)c1 * ldu + r] = r < d ? M1[j] : make_float2(0.f, 0.f);
+        }
+        if (a.U_out && r < d) {
+            float2* Uo = a.U_out + (size_t)sig * d * d + (size_t)r * d;
+            if (c0 < d) Uo[c0] = M0[j];
+            if (c1 < d) Uo[c1] = M1[j];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase D: G = U diag(l') U^H on 4x4 register tiles of the lower triangle
+    const int nt1 = (d + 3) / 4;
+    const int ntiles = nt1 * (nt1 + 1) / 2;
+    const float c1z = P ? P[P_C1Z] : 0.f;
+    float rsq = 0.f;
+    for (int t = tid; t < ntiles; t += NT) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        float2 acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int yv = 0; yv < 4; ++yv) acc[x][yv] = make_float2(0.f, 0.f);
+        const float4* Ua = reinterpret_cast<const float4*>(U + 4 * ti);
+        const float4* Ub = reinterpret_cast<const float4*>(U + 4 * tj);
+        const int ld4 = ldu / 2;   // float4 stride per column
+        for (int k = 0; k < d; ++k) {
+            const float lp = lamp[k];
+            const float4 a01 = Ua[(size_t)k * ld4], a23 = Ua[(size_t)k * ld4 + 1];
+            const float4 b01 = Ub[(size_t)k * ld4], b23 = Ub[(size_t)k * ld4 + 1];
+            const float2 av[4] = {make_float2(lp * a01.x, lp * a01.y), make_float2(lp * a01.z, lp * a01.w),
+                                  make_float2(lp * a23.x, lp * a23.y), make_float2(lp * a23.z, lp * a23.w)};
+            const float2 bv[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y),
+                                  make_float2(b23.z, b23.w)};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int yv = 0; yv < 4; ++yv) {
+                    acc[x][yv].x += av[x].x * bv[yv].x + av[x].y * bv[yv].y;
+                    acc[x][yv].y += av[x].y * bv[yv].x - av[x].x * bv[yv].y;
+                }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int i = 4 * ti + x;
+            if (i >= d) continue;
+#pragma unroll
+            for (int yv = 0; yv < 4; ++yv) {
+                const int j = 4 * tj + yv;
+                if (j > i) continue;
+                float2 g = acc[x][yv];
+                if (i == j) g.y = 0.f;
+                GV[pk(i, j)] = g;
+                if (a.with_c > 0) {
+                    float2 c = make_float2(0.f, 0.f);
+                    if (i == j) c.x = (i < n) ? hs[i] : c1z;
+                    else if (i == n) c = cconj(phis[j]);
+                    const float rx = g.x - c.x, ry = g.y - c.y;
+                    rsq += (i == j ? 1.f : 2.f) * (rx * rx + ry * ry);
+                }
+            }
+        }
+    }
+    if (a.with_c > 0) {
+        float v[1] = {rsq};
+        block_sum<1>(v, red);
+        if (tid == 0) a.r_out[sig] = sqrtf(v[0]);
+    }
+}
+
+// =====================================================================================
+// k_mean: deterministic sum of r over the chunk (double), one CTA.
+//   out_sum[0] = sum, and if mean_out != null, mean_out[0] = float(sum / count_total).
+// =====================================================================================
+__global__ void __launch_bounds__(1024) k_rsum(const float* __restrict__ r, int B, double* __restrict__ out_sum) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < B; i += 1024) acc += (double)r[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = red[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out_sum[0] = v;
+    }
+}
+__global__ void k_mean_from_sum(const double* __restrict__ sum, double count, float* __restrict__ mean_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) mean_out[0] = (float)(sum[0] / count);
+}
+
+// =====================================================================================
+// k_final_phi: phi of the last layer (admm_net.py:764) from the state left by layer K-2.
+// One warp per signal.
+// =====================================================================================
+struct FinalArgs {
+    const float2* y;
+    const float2* b;
+    const float2* Zp;
+    const float2* GV;
+    const float2* phi_prev;
+    const float* r_prev;
+    const float* mean_prev;
+    const float* Pk;     // last layer (rho_phi)
+    const float* Pkm1;   // layer K-2 (alpha)
+    float2* phi_out;
+    int B, n, d, first;
+};
+__global__ void __launch_bounds__(256) k_final_phi(FinalArgs a) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= a.B) return;
+    const int n = a.n, d = a.d, npk = d * (d + 1) / 2;
+    const float rho_phi = a.Pk[P_RHO_PHI];
+    float alpha = 0.f;
+    if (!a.first) alpha = z_alpha(a.Pkm1, a.r_prev[w], *a.mean_prev);
+    const float2* Zrow = a.Zp + (size_t)w * npk + pk(n, 0);
+    const float2* Grow = a.GV + (size_t)w * npk + pk(n, 0);
+    for (int j = lane; j < n; j += 32) {
+        float2 g = make_float2(0.f, 0.f), z = make_float2(0.f, 0.f);
+        if (!a.first) {
+            const float2 gr = Grow[j], zr = Zrow[j];
+            const float2 c = cconj(a.phi_prev[(size_t)w * n + j]);
+            const float2 zn = make_float2(zr.x + alpha * (gr.x - c.x), zr.y + alpha * (gr.y - c.y));
+            g = cconj(gr);
+            z = cconj(zn);
+        }
+        const float2 bj = a.b[(size_t)w * n + j], yj = a.y[(size_t)w * n + j];
+        const float ab = hypotf(bj.x, bj.y);
+        const float bsq = ab * ab + ADMM_EPS;
+        const float wgt = bsq / (1.f + rho_phi * bsq);
+        const float2 yob = cdiv(yj, make_float2(bj.x + ADMM_EPS, bj.y));
+        a.phi_out[(size_t)w * n + j] =
+            make_float2(wgt * (yob.x + rho_phi * g.x + z.x), wgt * (yob.y + rho_phi * g.y + z.y));
+    }
+}
+
+}  // namespace admmnet

@@ -1,0 +1,323 @@
+// Grid peak search (reference utils/peakSearchUtils.py:9-173, utils/mathUtils.py:4-21) in fp64.
+//
+//   surface  Z[iy][ix] = | sum_{p<yb} sum_{q<xb} conj(phi[p*xb+q]) e^{+j2pi fre_p(y_iy)} e^{-j2pi fre_q(x_ix)} |^2
+//            evaluated separably: T = S conj(Phi), Z = |T conj(D)^T|^2
+//   maxima   8-connected, plateau-aware, borders allowed (skimage.morphology.local_maxima semantics,
+//            oracle/peak_oracle.py::local_maxima), listed in row-major order (np.where)
+//   refine   `iter` rounds of np.arange windows around every peak, first-occurrence argmax
+//            (peakSearchUtils.py:136-171)
+//   top-L    stable sort by height, descending (main_for_net.py:119-126)
+// All grid positions are produced with numpy's arange/linspace arithmetic so that they are bit-identical
+// to the reference's; the double-precision sums differ from BLAS' order at the 1e-16 level only.
+#include "common.cuh"
+
+namespace admmnet {
+
+struct PeakArgs {
+    const void* phi;       // [B][n] complex64 or complex128
+    int phi_is_c128;
+    int B, xb, yb;         // n = xb*yb; x <-> tau uses xb, y <-> f uses yb
+    const double* axis_x;  // [Gx] coarse grid (np.arange on the host / caller)
+    const double* axis_y;  // [Gy]
+    int Gx, Gy;
+    double xmin, xmax, xstep, ymin, ymax, ystep, reducefactor;
+    int iters;
+    int pmax;              // capacity of peaks per signal
+    double* peaks;         // [B][pmax][3]  (x, y, height), discovery order
+    int* count;            // [B]
+    int topl;              // 0 = skip
+    double* top;           // [B][topl][3]
+    double* surface;       // optional [B][Gy][Gx]
+    int* status;
+};
+
+#define TWO_PI_D 6.283185307179586   // == 2*np.pi in binary64
+
+__device__ __forceinline__ double np_arange_val(double start, double step, int i) {
+    // numpy DOUBLE_fill: buf[0]=start, buf[1]=start+step, buf[i]=start+i*(buf[1]-buf[0])
+    if (i == 0) return start;
+    const double b1 = __dadd_rn(start, step);
+    if (i == 1) return b1;
+    const double delta = __dsub_rn(b1, start);
+    return __dadd_rn(start, __dmul_rn((double)i, delta));
+}
+__device__ __forceinline__ int np_arange_len(double start, double stop, double step) {
+    const double q = __ddiv_rn(__dsub_rn(stop, start), step);
+    const double c = ceil(q);
+    return c > 0.0 ? (c > 1.0e6 ? 1000000 : (int)c) : 0;
+}
+// vander_vec(0,(len-1)*v,len)[k] = exp(1j*2*pi*linspace(0,(len-1)*v,len)[k])
+__device__ __forceinline__ double2 steer(double v, int k, int len) {
+    double fre = 0.0;
+    if (len > 1) {
+        const double stop = __dmul_rn((double)(len - 1), v);
+        if (k == len - 1) fre = stop;
+        else {
+            const double step = __ddiv_rn(stop, (double)(len - 1));
+            fre = __dmul_rn((double)k, step);
+        }
+    }
+    const double th = __dmul_rn(TWO_PI_D, fre);
+    double s, c;
+    sincos(th, &s, &c);
+    return make_double2(c, s);
+}
+__device__ __forceinline__ double2 dmul(double2 a, double2 b) {
+    return make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)),
+                        __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ double abs2_np(double2 w) {
+    const double a = hypot(w.x, w.y);   // np.abs(.) ** 2
+    return a * a;
+}
+
+// value of the spectrum at one (x,y): | sum_p s_p(y) * conj( sum_q phi[p][q] d_q(x) ) |^2 ; phis in shared memory
+#define PEAK_MAX_BASE 32
+__device__ double spectrum_point(const double2* __restrict__ phis, int xb, int yb, double x, double y) {
+    double2 dq[PEAK_MAX_BASE];
+    for (int q = 0; q < xb; ++q) dq[q] = steer(x, q, xb);
+    double2 acc = make_double2(0.0, 0.0);
+    for (int p = 0; p < yb; ++p) {
+        const double2 sp = steer(y, p, yb);
+        double2 row = make_double2(0.0, 0.0);
+        for (int q = 0; q < xb; ++q) {
+            const double2 ph = phis[p * xb + q];
+            row.x += ph.x * dq[q].x - ph.y * dq[q].y;        // phi * d
+            row.y += ph.x * dq[q].y + ph.y * dq[q].x;
+        }
+        acc.x += row.x * sp.x + row.y * sp.y;                // conj(row) * s
+        acc.y += row.x * sp.y - row.y * sp.x;
+    }
+    return abs2_np(acc);
+}
+
+__host__ __device__ inline size_t peak_smem_bytes(int Gx, int Gy, int xb, int yb, int pmax) {
+    size_t dbl = (((size_t)Gx * Gy + 1) & ~(size_t)1)   // Z (padded: the double2 arrays behind it need 16 B alignment)
+                 + 2 * ((size_t)Gy * yb + (size_t)Gx * xb + (size_t)Gy * xb + (size_t)xb * yb)   // Sy, Dx, T, phi
+                 + 64;                      // reductions
+    size_t bytes = dbl * 8 + (size_t)Gx * Gy /*flags*/ + 16 + (256 + 8) * 4 /*scan*/ + (size_t)pmax * 4;
+    return (bytes + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Gx = a.Gx, Gy = a.Gy, xb = a.xb, yb = a.yb, n = xb * yb, N = Gx * Gy;
+    double* Z = reinterpret_cast<double*>(smem_raw);
+    double2* Sy = reinterpret_cast<double2*>(Z + ((N + 1) & ~1));   // [Gy][yb]
+    double2* Dx = Sy + (size_t)Gy * yb;                        // [Gx][xb]
+    double2* T = Dx + (size_t)Gx * xb;                         // [Gy][xb]
+    double2* phis = T + (size_t)Gy * xb;                       // [n]
+    double* redd = reinterpret_cast<double*>(phis + n);        // [64]
+    int* scan = reinterpret_cast<int*>(redd + 64);             // [256+8]
+    int* plist = scan + 256 + 8;                               // [pmax] flat pixel index of each peak
+    unsigned char* flag = reinterpret_cast<unsigned char*>(plist + a.pmax);   // [N]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int sig = blockIdx.x;
+
+    for (int i = tid; i < n; i += 256) {
+        if (a.phi_is_c128) phis[i] = reinterpret_cast<const double2*>(a.phi)[(size_t)sig * n + i];
+        else {
+            const float2 v = reinterpret_cast<const float2*>(a.phi)[(size_t)sig * n + i];
+            phis[i] = make_double2((double)v.x, (double)v.y);
+        }
+    }
+    for (int i = tid; i < Gy * yb; i += 256) Sy[i] = steer(a.axis_y[i / yb], i % yb, yb);
+    for (int i = tid; i < Gx * xb; i += 256) Dx[i] = steer(a.axis_x[i / xb], i % xb, xb);
+    __syncthreads();
+    // T[iy][q] = sum_p conj(phi[p][q]) * Sy[iy][p]
+    for (int i = tid; i < Gy * xb; i += 256) {
+        const int iy = i / xb, q = i % xb;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int p = 0; p < yb; ++p) {
+            const double2 ph = phis[p * xb + q], s = Sy[iy * yb + p];
+            acc.x += ph.x * s.x + ph.y * s.y;
+            acc.y += ph.x * s.y - ph.y * s.x;
+        }
+        T[i] = acc;
+    }
+    __syncthreads();
+    double lmin = INFINITY, lmax = -INFINITY;
+    for (int i = tid; i < N; i += 256) {
+        const int iy = i / Gx, ix = i % Gx;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int q = 0; q < xb; ++q) {
+            const double2 t = T[iy * xb + q], dq = Dx[ix * xb + q];
+            acc.x += t.x * dq.x + t.y * dq.y;
+            acc.y += t.y * dq.x - t.x * dq.y;
+        }
+        const double z = abs2_np(acc);
+        Z[i] = z;
+        lmin = fmin(lmin, z);
+        lmax = fmax(lmax, z);
+        if (a.surface) a.surface[(size_t)sig * N + i] = z;
+    }
+    // block min / max (constant image has no maxima)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if (lane == 0) { redd[wid] = lmin; redd[8 + wid] = lmax; }
+    __syncthreads();
+    double gmin = redd[0], gmax = redd[8];
+    for (int w = 1; w < 8; ++w) { gmin = fmin(gmin, redd[w]); gmax = fmax(gmax, redd[8 + w]); }
+    const bool constant = !(gmax > gmin);
+
+    // ---- candidates: no strictly greater 8-neighbour (outside the image counts as lower)
+    for (int i = tid; i < N; i += 256) {
+        const int iy = i / Gx, ix = i % Gx;
+        const double z = Z[i];
+        bool cand = !constant;
+        for (int dy = -1; dy <= 1 && cand; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = iy + dy, xx = ix + dx;
+                if ((dy | dx) == 0 || yy < 0 || yy >= Gy || xx < 0 || xx >= Gx) continue;
+                if (Z[yy * Gx + xx] > z) { cand = false; break; }
+            }
+        flag[i] = cand ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- plateaus: a candidate with an equal-valued non-candidate neighbour is not a maximum
+    for (int guard = 0; guard < N; ++guard) {
+        int changed = 0;
+        for (int i = tid; i < N; i += 256) {
+            if (!flag[i]) continue;
+            const int iy = i / Gx, ix = i % Gx;
+            const double z = Z[i];
+            bool kill = false;
+            for (int dy = -1; dy <= 1 && !kill; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int yy = iy + dy, xx = ix + dx;
+                    if ((dy | dx) == 0 || yy < 0 || yy >= Gy || xx < 0 || xx >= Gx) continue;
+                    if (Z[yy * Gx + xx] == z && !flag[yy * Gx + xx]) { kill = true; break; }
+                }
+            if (kill) { flag[i] = 0; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // ---- ordered compaction (row-major == np.where order)
+    const int seg = (N + 255) / 256;
+    const int s0 = min(N, tid * seg), s1 = min(N, s0 + seg);
+    int cnt = 0;
+    for (int i = s0; i < s1; ++i) cnt += flag[i];
+    scan[tid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < 256; ++t) { const int c = scan[t]; scan[t] = run; run += c; }
+        scan[256] = run;
+    }
+    __syncthreads();
+    const int P = scan[256];
+    const int Pst = min(P, a.pmax);
+    {
+        int o = scan[tid];
+        for (int i = s0; i < s1; ++i)
+            if (flag[i]) { if (o < a.pmax) plist[o] = i; ++o; }
+    }
+    if (tid == 0) {
+        a.count[sig] = P;
+        if (P > a.pmax) atomicOr(a.status, 2);
+    }
+    __syncthreads();
+
+    // ---- refinement: one warp per peak, lanes over the local grid points
+    double* out = a.peaks + (size_t)sig * a.pmax * 3;
+    for (int k = wid; k < Pst; k += 8) {
+        const int pix = plist[k];
+        double px = a.axis_x[pix % Gx], py = a.axis_y[pix / Gx], ph = 0.0;
+        double lx = a.xstep, ly = a.ystep;
+        for (int it = 0; it < a.iters; ++it) {
+            lx = __dmul_rn(a.reducefactor, lx);
+            ly = __dmul_rn(a.reducefactor, ly);
+            const double x0 = fmax(a.xmin, __dsub_rn(px, lx)), x1 = fmin(__dsub_rn(a.xmax, lx), __dadd_rn(px, lx));
+            const double y0 = fmax(a.ymin, __dsub_rn(py, ly)), y1 = fmin(__dsub_rn(a.ymax, ly), __dadd_rn(py, ly));
+            if (x0 >= x1 || y0 >= y1) continue;
+            const int nx = np_arange_len(x0, x1, lx), ny = np_arange_len(y0, y1, ly);
+            if (nx == 0 || ny == 0) continue;
+            double best = -INFINITY;
+            int bidx = 0x7fffffff;
+            for (int q = lane; q < nx * ny; q += 32) {
+                const double xv = np_arange_val(x0, lx, q % nx), yv = np_arange_val(y0, ly, q / nx);
+                const double z = spectrum_point(phis, xb, yb, xv, yv);
+                if (z > best) { best = z; bidx = q; }      // q increases: first occurrence kept
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+            }
+            if (bidx != 0x7fffffff) {
+                px = np_arange_val(x0, lx, bidx % nx);
+                py = np_arange_val(y0, ly, bidx / nx);
+                ph = best;
+            }
+        }
+        if (lane == 0) { out[3 * k] = px; out[3 * k + 1] = py; out[3 * k + 2] = ph; }
+    }
+    if (a.topl <= 0) return;
+    __syncthreads();
+    __threadfence_block();
+    // ---- top-L by height (stable: ties keep discovery order)
+    double* top = a.top + (size_t)sig * a.topl * 3;
+    unsigned char* taken = flag;   // reuse
+    for (int i = tid; i < Pst; i += 256) taken[i] = 0;
+    __syncthreads();
+    for (int l = 0; l < a.topl; ++l) {
+        double best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < Pst; i += 256)
+            if (!taken[i]) {
+                const double hgt = out[3 * i + 2];
+                if (hgt > best) { best = hgt; bi = i; }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { redd[wid] = best; scan[wid] = bi; }
+        __syncthreads();
+        double gb = redd[0];
+        int gi = scan[0];
+        for (int w = 1; w < 8; ++w) {
+            const double ob = redd[w];
+            const int oi = scan[w];
+            if (oi == 0x7fffffff) continue;
+            if (gi == 0x7fffffff || ob > gb || (ob == gb && oi < gi)) { gb = ob; gi = oi; }
+        }
+        if (tid == 0) {
+            if (gi != 0x7fffffff) {
+                top[3 * l] = out[3 * gi]; top[3 * l + 1] = out[3 * gi + 1]; top[3 * l + 2] = out[3 * gi + 2];
+                taken[gi] = 1;
+            } else {
+                top[3 * l] = 0.0; top[3 * l + 1] = 0.0; top[3 * l + 2] = 0.0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Spectrum at arbitrary points (peak_search(phi, X, x_base, Y, y_base) with non-tensor grids).
+__global__ void __launch_bounds__(256)
+k_peak_points(const void* phi, int phi_is_c128, int xb, int yb, const double* __restrict__ X,
+              const double* __restrict__ Y, int npts, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* phis = reinterpret_cast<double2*>(smem_raw);
+    const int n = xb * yb;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (phi_is_c128) phis[i] = reinterpret_cast<const double2*>(phi)[i];
+        else {
+            const float2 v = reinterpret_cast<const float2*>(phi)[i];
+            phis[i] = make_double2((double)v.x, (double)v.y);
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npts) out[i] = spectrum_point(phis, xb, yb, X[i], Y[i]);
+}
+
+}  // namespace admmnet

@@ -1,0 +1,2 @@
+"""Drop-in for the reference's top-level `admm_net` module (same import path): re-exports the B200 mirror."""
+from admmnet_b200.admm_net import ADMMNet, GLayer, HLayer, PhiEstADMMNet, PhiLayer, ZLayer  # noqa: F401

@@ -1,0 +1,119 @@
+/*
+ * admmnet_b200 — C ABI of the B200 (sm_100a) hot path of E-J408/admm-net.
+ *
+ * The reference has no FFI layer: the path sits behind three Python callables
+ * (SURVEY.md §8b).  This header is the boundary a binding would target; the Python mirror of the
+ * reference API in admm-net_b200/ (ctypes) is its only in-tree caller.  INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; admmnet_last_error() (thread local) explains.
+ *   - all data pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *     buffer; nothing is allocated behind the caller's back (query *_workspace_bytes first).
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); calls are re-entrant
+ *     across streams given distinct workspaces.  No C++ exception crosses the ABI.
+ *   - complex64 = interleaved float pairs, complex128 = interleaved double pairs, row-major.
+ */
+#ifndef ADMMNET_B200_H
+#define ADMMNET_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMMNET_OK 0
+#define ADMMNET_ERR_ARG (-1)
+#define ADMMNET_ERR_CUDA (-2)
+#define ADMMNET_ERR_WORKSPACE (-3)
+
+/* status word bits (admmnet_status / peak status) */
+#define ADMMNET_STATUS_EIGH_FAILED 1     /* QL did not converge or rotation stream overflowed rcap */
+#define ADMMNET_STATUS_PEAK_OVERFLOW 2   /* more local maxima than pmax (count[] still holds the true number) */
+
+const char* admmnet_last_error(void);
+int admmnet_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parameters.  One float record per layer, admmnet_param_stride(n) floats apart; layout in
+ * admm-net_b200/csrc/common.cuh (enum ParamOff), written by admm-net_b200/params.py from a
+ * reference-format state_dict (keys of admm_net.py:727-739).
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_param_stride(int n);
+
+/* ---------------------------------------------------------------------------------------------
+ * PhiEstADMMNet.forward  (replaces admm_net.py:742-764; layers: 79-105, 134-194, 237-354, 388-474)
+ *   y, b     complex64 [B][n], n = Mdim*Ndim <= 127
+ *   sigma    float32  [B]
+ *   params   float32  [K][admmnet_param_stride(n)]
+ *   phi_out  complex64 [B][n]
+ *   rcap     per-signal capacity of the plane-rotation stream (float2 entries), multiple of 1024;
+ *            0 selects the default 2*d*d rounded up.
+ * The ZLayer batch mean (admm_net.py:459) is taken over the B signals of this call, whatever `chunk` is:
+ * per-signal state (packed Z, G, phi, h, r: ~83 KB/signal at n=100) is kept for all B signals, the
+ * eigen-solver scratch (~200 KB/signal) only for `chunk` signals at a time (chunk <= 0: chunk = B).
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_forward_workspace_bytes(int B, int chunk, int n, int K, int rcap, size_t* bytes);
+int admmnet_forward(const void* y, const void* b, const float* sigma, int B, int chunk, int Mdim, int Ndim, int K,
+                    const float* params, void* phi_out, void* ws, size_t ws_bytes, int rcap, void* stream);
+
+/* Split-phase variant (what admmnet_forward loops over).  For exact whole-batch semantics across GPUs
+ * (SURVEY.md §8e): for each layer k < K-1 run admmnet_layer_chunk over the local chunks, then
+ * admmnet_layer_rsum(k), all-reduce *rsum[k] over the ranks, admmnet_set_mean(k, global count);
+ * finally admmnet_final_phi.  y/b/sigma are the full local arrays; sig_off/Bc select the chunk.     */
+int admmnet_layer_chunk(const void* y, const void* b, const float* sigma, int B, int chunk, int sig_off, int Bc,
+                        int Mdim, int Ndim, int K, int k, const float* params, void* ws, size_t ws_bytes, int rcap,
+                        void* stream);
+int admmnet_layer_rsum(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k, void* stream);
+int admmnet_ws_scalars(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, double** rsum,
+                       float** mean, int** status);
+int admmnet_set_mean(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k, double count,
+                     void* stream);
+int admmnet_final_phi(const void* y, const void* b, int B, int chunk, int Mdim, int Ndim, int K, const float* params,
+                      void* phi_out, void* ws, size_t ws_bytes, int rcap, void* stream);
+/* copies the status word to the host (synchronises the stream) */
+int admmnet_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream,
+                   int* status_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Unit taps of the eigen-solver (replaces torch.linalg.eigh + the two bmm of admm_net.py:303,349)
+ *   A        complex64 [B][d][d] row-major, lower triangle read, d <= 128
+ *   evals    float32 [B][d]   (QL order, not sorted)
+ *   evecs    complex64 [B][d][d] row-major, column i pairs with evals[i]       (may be NULL)
+ *   fn_out   complex64 [B][d(d+1)/2] packed lower (row-major) f(A) = U diag(f(l)) U^H (may be NULL)
+ *   params   one layer record: f = the learned eigenvalue map (admm_net.py:310-334); NULL: f = id
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_eigh_workspace_bytes(int B, int d, int rcap, size_t* bytes);
+int admmnet_eigh_batched(const void* A, int B, int d, float* evals, void* evecs, void* fn_out, const float* params,
+                         void* ws, size_t ws_bytes, int rcap, void* stream, int* status_dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Classical ADMM  (replaces admm.py:6-114 admm_for_us; see SURVEY.md App. A.3 for why the solver
+ * is the linear recursion phi_k = M^-1 (y/b + rho phi_{k-1}) for every reachable input)
+ *   y, b     complex128 (in_is_c128=1) or complex64 [B][n], n <= 256
+ *   phi_out  complex128 [B][n]
+ * ------------------------------------------------------------------------------------------- */
+int admm_classic_forward(const void* y, const void* b, int in_is_c128, int B, int n, double rho, int n_iter,
+                         void* phi_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Peak search  (replaces utils/peakSearchUtils.py:9-60 peak_search[_func] and 63-173 alt_peak_search)
+ *   phi       complex64/complex128 [B][xbase*ybase]
+ *   axis_x/y  float64 coarse grid axes (np.arange(xmin, xmax-xstep, xstep), np.arange(ymin, ymax-xstep, ystep))
+ *   peaks     float64 [B][pmax][3] rows (x, y, height) in row-major discovery order; count[B] = #maxima
+ *   top       float64 [B][topl][3] best topl rows by height (stable), zero padded; topl = 0 skips it
+ *   surface   optional float64 [B][Gy][Gx]
+ * ------------------------------------------------------------------------------------------- */
+int peak_search_full(const void* phi, int phi_is_c128, int B, int xbase, int ybase, const double* axis_x, int Gx,
+                     const double* axis_y, int Gy, double xmin, double xmax, double xstep, double ymin, double ymax,
+                     double ystep, double reducefactor, int iters, int pmax, double* peaks, int* count, int topl,
+                     double* top, double* surface, int* status_dev, void* stream);
+/* spectrum of ONE phi at npts arbitrary (x,y) points: peak_search(phi, X, x_base, Y, y_base) */
+int peak_search_points(const void* phi, int phi_is_c128, int xbase, int ybase, const double* X, const double* Y,
+                       int npts, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
