@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/admmnet_b200.h"
 #include "net_kernels.cu"
@@ -21,6 +22,68 @@ static int fail(int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                           \
             return fail(ADMMNET_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
     } while (0)
+
+// ------------------------------------------------------------------------------------ profiling hooks
+// Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
+// Process-global, not thread safe; off by default (then the only cost is one branch per launch).
+namespace prof {
+enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, NKINDS };
+static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search"};
+struct Rec { int kind; cudaEvent_t a, b; };
+static bool on = false;
+static std::vector<Rec> recs;
+static std::vector<cudaEvent_t> pool;
+static size_t pool_used = 0;
+static cudaEvent_t get_event() {
+    if (pool_used == pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        pool.push_back(e);
+    }
+    return pool[pool_used++];
+}
+struct Scope {
+    cudaStream_t st;
+    bool active;
+    Scope(int kind, cudaStream_t s) : st(s), active(on) {
+        if (active) {
+            Rec r{kind, get_event(), get_event()};
+            cudaEventRecord(r.a, st);
+            recs.push_back(r);
+        }
+    }
+    ~Scope() {
+        if (active) cudaEventRecord(recs.back().b, st);
+    }
+};
+}  // namespace prof
+
+extern "C" int admmnet_profile_begin(void) {
+    prof::recs.clear();
+    prof::pool_used = 0;
+    prof::on = true;
+    return 0;
+}
+extern "C" int admmnet_profile_kinds(void) { return prof::NKINDS; }
+extern "C" const char* admmnet_profile_kind_name(int kind) {
+    return (kind >= 0 && kind < prof::NKINDS) ? prof::kNames[kind] : "";
+}
+// ms[kind] = summed device time of that kind's launches since admmnet_profile_begin, launches[kind] = count
+extern "C" int admmnet_profile_end(double* ms, long long* launches) {
+    prof::on = false;
+    if (!ms || !launches) return fail(ADMMNET_ERR_ARG, "null pointer");
+    for (int k = 0; k < prof::NKINDS; ++k) { ms[k] = 0.0; launches[k] = 0; }
+    for (auto& r : prof::recs) {
+        CK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.kind] += t;
+        launches[r.kind] += 1;
+    }
+    prof::recs.clear();
+    prof::pool_used = 0;
+    return 0;
+}
 
 extern "C" const char* admmnet_last_error(void) { return g_err.c_str(); }
 extern "C" int admmnet_version(void) { return 100; }
@@ -80,6 +143,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
     {
         const size_t sm = (size_t)2 * d * QL_THREADS * sizeof(double);
         CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
                                                                          status);
         CK(cudaGetLastError());
@@ -87,6 +151,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
     {
         const size_t sm = (size_t)2 * ROT_CHUNK * sizeof(float2) + (size_t)d * (d | 1) * sizeof(float);
         CK(cudaFuncSetAttribute(k_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        prof::Scope pscope(prof::ROT, st);
         k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr);
         CK(cudaGetLastError());
     }
@@ -96,6 +161,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         t.Pk = Pk; t.r_out = w.r; t.U_out = U_out; t.lamp_out = lamp_out;
         t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c;
         const size_t sm = tail_smem_bytes(d, t.ldu);
+        prof::Scope pscope(prof::TAIL, st);
         if (d <= 104) {
             CK(cudaFuncSetAttribute(k_tail<13, 416>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_tail<13, 416><<<B, 416, sm, st>>>(t);
@@ -162,7 +228,10 @@ extern "C" int admmnet_layer_chunk(const void* y, const void* b, const float* si
     h.B = Bc; h.n = n; h.d = d; h.ld = d | 1; h.first = (k == 0);
     const size_t sm = head_smem_bytes(d, h.ld);
     CK(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_head<<<Bc, 256, sm, st>>>(h);
+    {
+        prof::Scope pscope(prof::HEAD, st);
+        k_head<<<Bc, 256, sm, st>>>(h);
+    }
     CK(cudaGetLastError());
     return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st);
 }
@@ -173,6 +242,7 @@ extern "C" int admmnet_layer_rsum(void* ws, size_t ws_bytes, int B, int chunk, i
     if (k < 0 || k >= K) return fail(ADMMNET_ERR_ARG, "k out of range");
     Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
     if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
     k_rsum<<<1, 1024, 0, (cudaStream_t)stream>>>(w.r, B, w.rsum + k);
     CK(cudaGetLastError());
     return 0;
@@ -184,6 +254,7 @@ extern "C" int admmnet_set_mean(void* ws, size_t ws_bytes, int B, int chunk, int
     if (k < 0 || k >= K) return fail(ADMMNET_ERR_ARG, "k out of range");
     Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
     if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
     k_mean_from_sum<<<1, 32, 0, (cudaStream_t)stream>>>(w.rsum + k, count, w.mean + k);
     CK(cudaGetLastError());
     return 0;
@@ -205,6 +276,7 @@ extern "C" int admmnet_final_phi(const void* y, const void* b, int B, int chunk,
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 1) CK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
     const long long nthreads = (long long)B * 32;
+    prof::Scope pscope(prof::MISC, st);
     k_final_phi<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(f);
     CK(cudaGetLastError());
     return 0;
@@ -277,7 +349,8 @@ extern "C" int admm_classic_forward(const void* y, const void* b, int in_is_c128
     if (!y || !b || !phi_out) return fail(ADMMNET_ERR_ARG, "null pointer");
     if (B <= 0 || n <= 0 || n > 256 || n_iter < 0) return fail(ADMMNET_ERR_ARG, "need B > 0, 0 < n <= 256, n_iter >= 0");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (B * 32 + 255) / 256;
+    const int grid = (int)(((long long)B * 32 + 255) / 256);
+    prof::Scope pscope(prof::CLASSIC, st);
     if (n <= 128) {
         if (in_is_c128) k_classic<double2, 4><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
         else k_classic<float2, 4><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
@@ -309,6 +382,7 @@ extern "C" int peak_search_full(const void* phi, int phi_is_c128, int B, int xba
     a.reducefactor = reducefactor; a.iters = iters; a.pmax = pmax; a.peaks = peaks; a.count = count;
     a.topl = topl; a.top = top; a.surface = surface; a.status = status_dev;
     CK(cudaFuncSetAttribute(k_peak_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    prof::Scope pscope(prof::PEAK, (cudaStream_t)stream);
     k_peak_search<<<B, 256, sm, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return 0;
@@ -323,5 +397,29 @@ extern "C" int peak_search_points(const void* phi, int phi_is_c128, int xbase, i
     const size_t sm = (size_t)xbase * ybase * sizeof(double2);
     k_peak_points<<<(npts + 255) / 256, 256, sm, (cudaStream_t)stream>>>(phi, phi_is_c128, xbase, ybase, X, Y, npts, out);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ FP32 FMA peak
+// Roofline denominator for the FP32-pipe-bound eigen-solver kernels (MEASURED_PEAKS.json has no FP32
+// figure): 8 independent FFMA chains per thread, grid = 148*8 CTAs of 256 threads.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+// out must hold grid*256 floats; returns the flop count of one launch in *flops
+extern "C" int admmnet_fp32_peak_launch(float* out, int grid, int iters, double* flops, void* stream) {
+    if (!out || grid <= 0 || iters <= 0) return fail(ADMMNET_ERR_ARG, "bad arguments");
+    k_fma_peak<<<grid, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+    CK(cudaGetLastError());
+    if (flops) *flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
     return 0;
 }

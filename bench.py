@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json: signals/s for the K-layer ADMM-Net
+forward + peak search at 1/2/4/8 B200, % of roofline, reference CPU path beside it).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's algorithm on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] — ADMM-Net K=10, n = 10x10, forward + alt_peak_search
+(99x99 coarse grid, iter=3, top-3), synthetic signals of generate_data.py's recipe.  Weak scaling: every
+rank processes --per-gpu signals per step (default 131072 = the per-GPU share of the 1M batch at 8 GPUs),
+so at N=8 one step IS the 1M-signal configuration.  No collective on the data path (norm_scope='shard':
+the ZLayer batch mean is taken over each rank's shard; --norm-scope global adds 9 scalar all-reduces).
+One step = one pass over the batch; timed with CUDA events between barriers, max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_LAYERS, M, N, TOPL = 10, 10, 10, 3
+PEAK_OPTS = dict(xstep=0.01, ystep=0.01, iter=3)          # main_for_net.py:112-116
+METRIC = "signals/s, ADMM-Net K=10 forward + peak search"
+# SURVEY.md §8d algorithmic work per signal at n=100 (d=101)
+FLOP_PER_LAYER = 33.1e6          # eigh 24 d^3 + rebuild 8 d^3 + 0.15 MFLOP elementwise
+FLOP_PEAK_SEARCH = 0.86e6        # separable coarse surface
+BYTES_PER_SIGNAL = 2404          # y 800 + b 800 + sigma 4 in, phi 800 out
+
+
+def tile_signals(B, seed):
+    """generate_data.py-recipe signals (oracle/signals.py is only the INPUT generator here); 4096 unique
+    signals tiled to B with a per-copy global phase so no two signals are identical."""
+    from oracle import signals
+    base = min(B, 4096)
+    y, b, s, _ = signals.generate(base, seed=seed)
+    reps = (B + base - 1) // base
+    if reps > 1:
+        rng = np.random.default_rng(seed + 1)
+        ph = np.exp(1j * rng.uniform(0, 2 * np.pi, reps)).astype(np.complex64)
+        y = (y[None] * ph[:, None, None]).reshape(-1, y.shape[1])[:B]
+        b = np.tile(b, (reps, 1))[:B]
+        s = np.tile(s, reps)[:B]
+    return np.ascontiguousarray(y), np.ascontiguousarray(b), np.ascontiguousarray(s)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_sample(n_fwd, n_peak, threads, pool=None):
+    """The reference's algorithm on the host: oracle port of the forward (torch CPU, `threads` intra-op
+    threads) on n_fwd signals + literal port of alt_peak_search on n_peak signals (one per worker)."""
+    from oracle import net_oracle, peak_oracle, signals
+    import admmnet_b200
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = admmnet_b200.PhiEstADMMNet(M, N, 3, K_LAYERS).state_dict()
+    y, b, s, _ = signals.generate(n_fwd, seed=99)
+    yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
+    t0 = time.perf_counter()
+    phi = net_oracle.forward(sd, yt, bt, st, M, N, K_LAYERS).numpy()
+    t_f = time.perf_counter() - t0
+    jobs = [phi[i % n_fwd] for i in range(n_peak)]
+    t0 = time.perf_counter()
+    if pool is not None:
+        pool.map(_peak_job, jobs)
+    else:
+        for j in jobs:
+            _peak_job(j)
+    t_p = time.perf_counter() - t0
+    per_signal = t_f / n_fwd + t_p / n_peak
+    return 1.0 / per_signal, t_f, t_p
+
+
+def _peak_job(phi):
+    from oracle import peak_oracle
+    r = peak_oracle.alt_peak_search({"phi": phi, "xbase": N, "ybase": M}, PEAK_OPTS)
+    return peak_oracle.top_l(r, TOPL)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_fwd, n_peak = 256, max(cores, 2)
+    vals, times = [], []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            v, tf, tp = cpu_sample(n_fwd, n_peak, cores, pool)
+            if i >= args.warmup:
+                vals.append(v)
+                times.append(time.perf_counter() - t0)
+    v = float(np.mean(vals))
+    sample = (f"per step: oracle port of PhiEstADMMNet.forward (torch CPU, {cores} threads, no_grad) on {n_fwd} signals + "
+              f"literal port of alt_peak_search (99x99, iter=3) on {n_peak} signals over {cores} processes; "
+              "signals/s = 1/(t_fwd/n_fwd + t_peak/n_peak)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "signals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": "signals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "signals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE.json configs[2]: ADMM-Net K={K_LAYERS}, n={M}x{N}, forward + alt_peak_search "
+                        f"(99x99, iter=3, top-{TOPL}); {args.per_gpu} signals per GPU per step (1M/8), weak scaling",
+            "per_gpu_batch": args.per_gpu, "chunk": args.chunk, "norm_scope": args.norm_scope,
+            "l2": "working set per step (>10 GB of per-signal state) exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--per-gpu", type=int, default=131072)
+    ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--norm-scope", default="shard", choices=["shard", "global"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import admmnet_b200
+    from admmnet_b200 import _capi, sharding
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _capi.lib()
+
+    B = args.per_gpu
+    torch.manual_seed(0)
+    model = admmnet_b200.PhiEstADMMNet(M, N, 3, K_LAYERS).eval()
+    model.chunk = args.chunk
+    model.check_status = False               # status word is read once after the timed region
+    y, b, s = tile_signals(B, seed=1234 + rank)
+    yh, bh, sh = (torch.from_numpy(a).pin_memory() for a in (y, b, s))
+    yd, bd, sd_ = yh.to(dev), bh.to(dev), sh.to(dev)
+    phi_h = torch.empty(B, M * N, dtype=torch.complex64).pin_memory()
+    top_h = torch.empty(B, TOPL, 3, dtype=torch.float64).pin_memory()
+    cnt_h = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def step_device(y_, b_, s_):
+        if args.norm_scope == "global" and world > 1:
+            phi = sharding.sharded_forward(model, y_, b_, s_, "global")
+        else:
+            phi = model.forward_device(y_, b_, s_)
+        pk = admmnet_b200.alt_peak_search_batched(phi, N, M, PEAK_OPTS, topl=TOPL, pmax=256)
+        return phi, pk
+
+    def step_e2e():
+        y_, b_, s_ = yh.to(dev, non_blocking=True), bh.to(dev, non_blocking=True), sh.to(dev, non_blocking=True)
+        phi, pk = step_device(y_, b_, s_)
+        phi_h.copy_(phi, non_blocking=True)
+        top_h.copy_(pk["top"], non_blocking=True)
+        cnt_h.copy_(pk["count"], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device(yd, bd, sd_)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    nk = L.admmnet_profile_kinds()
+    L.admmnet_profile_begin()
+    ms_total = timed(lambda: step_device(yd, bd, sd_), args.steps)
+    kms = (C.c_double * nk)()
+    kln = (C.c_longlong * nk)()
+    _capi.check(L.admmnet_profile_end(kms, kln))
+    clocks = sampler.stop() if rank == 0 else None
+    # status of the last forward (eigen-solver convergence) and of the run as a whole
+    ws = model._ws
+    st = C.c_int(0)
+    _capi.check(L.admmnet_status(ws.ptr, ws.nbytes, ws.B, ws.chunk, ws.n, ws.K, ws.rcap,
+                                 torch.cuda.current_stream().cuda_stream, C.byref(st)))
+    assert st.value == 0, f"eigen-solver status {st.value}"
+
+    # end-to-end through the public API with host buffers
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
+    e2e_steps = max(1, min(args.steps, 3))
+
+    # FP32 FMA peak (roofline denominator), timed alone
+    outp = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
+    flops = C.c_double()
+    stream = torch.cuda.current_stream().cuda_stream
+    L.admmnet_fp32_peak_launch(outp.data_ptr(), 148 * 8, 2000, C.byref(flops), stream)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.admmnet_fp32_peak_launch(outp.data_ptr(), 148 * 8, 2000, C.byref(flops), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    fp32_peak_tflops = flops.value / (best * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    names = [L.admmnet_profile_kind_name(i).decode() for i in range(nk)]
+    kern = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kln[i] / args.steps} for i in range(nk) if kln[i]}
+    gpu_ms = sum(v["ms_per_step"] for v in kern.values())
+    for v in kern.values():
+        v["share"] = v["ms_per_step"] / gpu_ms
+    eig = ("k_head", "k_ql", "k_rot", "k_tail")
+    eig_ms = sum(kern[k]["ms_per_step"] for k in eig if k in kern)
+    eig_launch = sum(kern[k]["launches_per_step"] for k in eig if k in kern)
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    achieved = FLOP_PER_LAYER * (K_LAYERS - 1) * B / (eig_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": "signals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": world * B / (ms_e2e / e2e_steps * 1e-3), "unit": "signals/s",
+                "h2d_bytes_per_step": int(yh.nbytes + bh.nbytes + sh.nbytes),
+                "d2h_bytes_per_step": int(phi_h.nbytes + top_h.nbytes + cnt_h.nbytes)},
+        "gpu_launches": int(sum(kln[i] for i in range(nk))),
+        "roofline": {
+            "bound": "fp32", "kernel": "layer pipeline k_head+k_ql+k_rot+k_tail (dominant: %s)" % dom,
+            "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
+            "traffic": None,
+            "note": "FP32-FMA/shared-memory bound eigen-solver (SURVEY.md §8d): algorithmic 33.1 MFLOP per signal-layer x "
+                    "(K-1) layers / summed CUDA-event time of the four kernels; peak = FP32 FFMA micro-kernel measured "
+                    "live (MEASURED_PEAKS.json has no FP32 figure). launches per step: %d" % eig_launch,
+            "hbm": {"achieved_gbs": BYTES_PER_SIGNAL * B / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                    "peak_source": "measured" if peaks else "fallback"},
+            "kernels": kern},
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, tf, tp = cpu_sample(192, 4, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "signals/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle port of the forward on 192 signals ({tf:.1f} s, {cores} torch threads) + "
+                                          f"literal port of alt_peak_search on 4 signals ({tp:.1f} s, 1 thread); "
+                                          "signals/s = 1/(t_fwd/192 + t_peak/4)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

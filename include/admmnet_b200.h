@@ -113,6 +113,18 @@ int peak_search_full(const void* phi, int phi_is_c128, int B, int xbase, int yba
 int peak_search_points(const void* phi, int phi_is_c128, int xbase, int ybase, const double* X, const double* Y,
                        int npts, double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): per-kernel CUDA-event timing of the launches issued between
+ * admmnet_profile_begin and admmnet_profile_end (summed ms and launch count per kernel kind), and an
+ * FP32-FMA peak micro-kernel (roofline denominator of the FP32-pipe-bound eigen-solver kernels).
+ * Process-global, not thread safe.
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_profile_begin(void);
+int admmnet_profile_kinds(void);
+const char* admmnet_profile_kind_name(int kind);
+int admmnet_profile_end(double* ms, long long* launches);
+int admmnet_fp32_peak_launch(float* out, int grid, int iters, double* flops, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

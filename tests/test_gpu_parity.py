@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box): CUDA path, called through the C ABI (ctypes), against the
+golden vectors of the reference and against the CPU oracle on the same seeded inputs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, load_net_case, parse_opts, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# BASELINE.json north_star: 1e-4 relative on the recovered phi (max-norm per signal)
+PHI_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import admmnet_b200
+    admmnet_b200._capi.lib()          # raises if the extension is missing: no silent fallback
+    return admmnet_b200
+
+
+def _eigh(pkg, A, params=None, vecs=True, fn=False):
+    from admmnet_b200 import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda")
+    B, d, _ = A.shape
+    nb = C.c_size_t()
+    _capi.check(L.admmnet_eigh_workspace_bytes(B, d, 0, C.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    ev = torch.empty(B, d, dtype=torch.float32, device=dev)
+    U = torch.empty(B, d, d, dtype=torch.complex64, device=dev) if vecs else None
+    G = torch.empty(B, d * (d + 1) // 2, dtype=torch.complex64, device=dev) if fn else None
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    Ad = A.to(dev).contiguous()
+    _capi.check(L.admmnet_eigh_batched(Ad.data_ptr(), B, d, ev.data_ptr(), U.data_ptr() if vecs else None,
+                                       G.data_ptr() if fn else None, params.data_ptr() if params is not None else None,
+                                       ws.data_ptr(), nb.value, 0, torch.cuda.current_stream().cuda_stream,
+                                       st.data_ptr()))
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    return ev.cpu(), U.cpu() if vecs else None, G.cpu() if fn else None
+
+
+def _unpack(Gp, d):
+    B = Gp.shape[0]
+    G = torch.zeros(B, d, d, dtype=Gp.dtype)
+    i, j = torch.tril_indices(d, d)
+    G[:, i, j] = Gp
+    G[:, j, i] = Gp.conj()
+    G[:, torch.arange(d), torch.arange(d)] = Gp[:, (torch.arange(d) * (torch.arange(d) + 3)) // 2]
+    return G
+
+
+@pytest.mark.parametrize("d", [3, 4, 17, 65, 101, 104, 105, 128])
+def test_eigh_random_hermitian(pkg, d):
+    torch.manual_seed(d)
+    X = torch.randn(5, d, d, dtype=torch.complex64)
+    A = 0.5 * (X + X.transpose(1, 2).conj())
+    ev, U, _ = _eigh(pkg, A)
+    scale = torch.linalg.matrix_norm(A, ord=2).max().item()
+    assert (A @ U - U * ev.unsqueeze(1).to(torch.complex64)).abs().amax() < 2e-5 * scale
+    assert (U.transpose(1, 2).conj() @ U - torch.eye(d)).abs().amax() < 1e-5
+    w = torch.linalg.eigvalsh(A.to(torch.complex128)).float()
+    assert (ev.sort(dim=1)[0] - w).abs().amax() < 1e-5 * scale
+
+
+def test_eigh_structured_cases(pkg):
+    d = 101
+    eye = torch.eye(d, dtype=torch.complex64)
+    diag = torch.diag(torch.linspace(-3, 5, d)).to(torch.complex64)
+    arrow = torch.diag(torch.full((d,), 0.01)).to(torch.complex64)          # layer-0 matrix: arrowhead
+    v = torch.randn(d - 1, dtype=torch.complex64)
+    arrow[:-1, -1] = v
+    arrow[-1, :-1] = v.conj()
+    arrow[-1, -1] = 1.8
+    rank1 = torch.outer(v.new_ones(d), v.new_ones(d))                       # repeated zero eigenvalue
+    A = torch.stack([eye, diag, arrow, rank1, torch.zeros(d, d, dtype=torch.complex64)])
+    ev, U, _ = _eigh(pkg, A)
+    assert (A @ U - U * ev.unsqueeze(1).to(torch.complex64)).abs().amax() < 2e-4
+    assert (U.transpose(1, 2).conj() @ U - torch.eye(d)).abs().amax() < 1e-5
+    w = torch.linalg.eigvalsh(A.to(torch.complex128)).float()
+    assert (ev.sort(dim=1)[0] - w).abs().amax() < 2e-5 * 101
+
+
+def test_hermitian_function_matches_oracle(pkg):
+    """f(A) = U f(L) U^H with the learned eigenvalue map: basis-invariant, compared with torch fp64."""
+    from admmnet_b200.params import pack_state_dict
+    from oracle import net_oracle
+    z, sd = load_net_case("pert_k10")
+    P = pack_state_dict(sd, 100, 10).cuda()
+    torch.manual_seed(1)
+    d = 101
+    X = torch.randn(4, d, d, dtype=torch.complex64) * 0.3
+    A = 0.5 * (X + X.transpose(1, 2).conj())
+    _, _, Gp = _eigh(pkg, A, params=P[3], vecs=False, fn=True)
+    G = _unpack(Gp, d)
+    w, U = torch.linalg.eigh(A.to(torch.complex128))
+    fw = net_oracle.eig_map(w.float(), net_oracle.layer_params(sd, 3)["g"]).to(torch.complex128)
+    Gt = (U * fw.unsqueeze(1)) @ U.transpose(1, 2).conj()
+    assert (G.to(torch.complex128) - Gt).abs().amax() / Gt.abs().amax() < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["init_k10", "pert_k10", "pert_k5"])
+def test_forward_matches_reference_golden(pkg, tag):
+    z, sd = load_net_case(tag)
+    K = int(z["K"])
+    net = pkg.PhiEstADMMNet(10, 10, 3, K).eval()
+    net.load_state_dict(sd)
+    y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
+    with torch.no_grad():
+        phi = net(y, b, s)
+    assert phi.dtype == torch.complex64 and phi.device.type == "cpu" and phi.shape == (7, 100)
+    assert rel_err(phi.numpy(), z["phi_batch"]).max() < PHI_TOL
+    # the data.npz signal alone with sigma [1,1] (main_for_net.py:93): config 1 of BASELINE.json
+    with torch.no_grad():
+        phi1 = net(y[:1], b[:1], s[:1].reshape(1, 1))
+    assert rel_err(phi1.numpy(), z["phi_single"]).max() < PHI_TOL
+    # every prefix depth (phi after layer k) against the reference's per-layer taps
+    for kk in range(1, K):
+        sub = pkg.PhiEstADMMNet(10, 10, 3, kk)
+        sub.load_state_dict({k_: v for k_, v in sd.items() if int(k_.split(".")[1]) < kk})
+        with torch.no_grad():
+            pk = sub(y, b, s).numpy()
+        assert rel_err(pk, z["batch_phi_layers"][kk - 1]).max() < PHI_TOL, kk
+
+
+def test_forward_vs_oracle_seeded_batch_and_scopes(pkg):
+    from oracle import net_oracle, signals
+    torch.manual_seed(3)
+    net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
+    y, b, s, _ = signals.generate(96, seed=17)
+    yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
+    ref = net_oracle.forward(net.state_dict(), yt, bt, st, 10, 10, 10)
+    with torch.no_grad():
+        phi = net(yt.cuda(), bt.cuda(), st.cuda())
+    assert phi.is_cuda
+    assert rel_err(phi.cpu().numpy(), ref.numpy()).max() < PHI_TOL
+    # exact whole-batch semantics must not depend on the scratch chunking
+    net.chunk = 40
+    with torch.no_grad():
+        phi_c = net(yt, bt, st)
+    assert rel_err(phi_c.numpy(), ref.numpy()).max() < PHI_TOL
+    assert rel_err(phi_c.numpy(), phi.cpu().numpy()).max() < 1e-5
+    # norm_scope='chunk': independent chunks == the reference run per chunk
+    net.norm_scope = "chunk"
+    net.chunk = 32
+    ref_c = net_oracle.forward(net.state_dict(), yt, bt, st, 10, 10, 10, chunk=32)
+    with torch.no_grad():
+        phi_s = net(yt, bt, st)
+    assert rel_err(phi_s.numpy(), ref_c.numpy()).max() < PHI_TOL
+    assert rel_err(ref_c.numpy(), ref.numpy()).max() > PHI_TOL      # the coupling is material
+
+
+def test_forward_other_shapes_and_edges(pkg):
+    from oracle import net_oracle, signals
+    torch.manual_seed(5)
+    for (M, N, K, B) in [(8, 8, 3, 5), (4, 6, 4, 3), (10, 10, 1, 4), (10, 10, 2, 1), (11, 11, 3, 2)]:
+        net = pkg.PhiEstADMMNet(M, N, 3, K).eval()
+        y, b, s, _ = signals.generate(B, Nb=M, Nd=N, seed=M * 100 + N)
+        yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
+        ref = net_oracle.forward(net.state_dict(), yt, bt, st, M, N, K)
+        with torch.no_grad():
+            phi = net(yt, bt, st)
+        assert rel_err(phi.numpy(), ref.numpy()).max() < PHI_TOL, (M, N, K)
+    net = pkg.PhiEstADMMNet(10, 10, 3, 2)
+    with pytest.raises(ValueError):
+        net(torch.zeros(2, 99, dtype=torch.complex64), torch.zeros(2, 99, dtype=torch.complex64), torch.ones(2))
+    with pytest.raises(Exception):
+        pkg.PhiEstADMMNet(12, 12, 3, 2)(torch.ones(1, 144, dtype=torch.complex64),
+                                       torch.ones(1, 144, dtype=torch.complex64), torch.ones(1))   # n > 127
+
+
+def test_linearity_free_property_large_batch(pkg):
+    """Size-independent property at a bench-sized batch: with norm_scope='chunk' the result for a signal
+    depends only on its own chunk, so permuting whole chunks permutes the output bit-exactly, and
+    duplicated signals give duplicated outputs."""
+    from oracle import signals
+    torch.manual_seed(0)
+    net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
+    net.norm_scope, net.chunk = "chunk", 256
+    y, b, s, _ = signals.generate(256, seed=1)
+    yt = torch.from_numpy(np.tile(y, (8, 1))).cuda()
+    bt = torch.from_numpy(np.tile(b, (8, 1))).cuda()
+    st = torch.from_numpy(np.tile(s, 8)).cuda()
+    with torch.no_grad():
+        phi = net(yt, bt, st)
+    phi = phi.reshape(8, 256, 100)
+    assert torch.isfinite(phi.real).all()
+    for c in range(1, 8):
+        assert torch.equal(phi[c], phi[0])
+
+
+def test_classic_matches_reference_golden_and_oracle(pkg):
+    from oracle import classic_oracle, signals
+    z = np.load(os.path.join(GOLDEN, "classic.npz"))
+    for c in range(len(z["iters"])):
+        i = int(z["case_sig"][c])
+        opts = dict(rho=float(z["case_rho"][c]), max_iter=int(z["case_max_iter"][c]))
+        phi, it = pkg.admm_for_us(z["y"][i], z["b"][i], 10, 10, 1.0, float(z["sigma"][i]), opts,
+                                  bool(z["case_use_min_iter"][c]), int(z["case_min_iter"][c]))
+        assert it == int(z["iters"][c])
+        assert phi.dtype == np.complex128 and phi.shape == (100,)
+        assert rel_err(phi, z["phi"][c]) < 1e-12
+    for n, B, dt in [(100, 1000, torch.complex128), (100, 257, torch.complex64), (256, 33, torch.complex128), (7, 5, torch.complex64)]:
+        y, b, _, _ = signals.generate(B, Nb=n, Nd=1, seed=n)
+        yt, bt = torch.from_numpy(y).to(dt).cuda(), torch.from_numpy(b).to(dt).cuda()
+        out = pkg.admm_for_us_batched(yt, bt, rho=0.7, n_iter=5).cpu().numpy()
+        ref = classic_oracle.admm_linear_recursion(yt.cpu().numpy(), bt.cpu().numpy(), 0.7, 5)
+        assert rel_err(out, ref).max() < 1e-12
+
+
+def test_peak_search_matches_reference_golden(pkg):
+    z = np.load(os.path.join(GOLDEN, "peaks.npz"))
+    names = sorted({k.split("__")[0] for k in z.files if "__" in k})
+    for name in names:
+        opts = parse_opts(z[f"{name}__opts"])
+        got = pkg.alt_peak_search({"phi": z[f"{name}__phi"], "xbase": 10, "ybase": 10}, opts)
+        exp = z[f"{name}__peaks"]
+        assert got.shape == exp.shape and got.dtype == np.float64, name
+        assert np.array_equal(got[:, :2], exp[:, :2]), name          # grid positions: bit exact
+        np.testing.assert_allclose(got[:, 2], exp[:, 2], rtol=1e-12, atol=1e-300)
+    ax = np.arange(0, 1 - 0.01, 0.01)
+    ay = np.arange(-0.5, 0.5 - 0.01, 0.01)
+    AX, AY = np.meshgrid(ax, ay)
+    surf = pkg.peak_search(z["net0__phi"], AX, 10, AY, 10)
+    np.testing.assert_allclose(surf, z["surface_net0"], rtol=1e-11, atol=1e-18)
+    v = pkg.peak_search_func(z["net0__phi"], 0.3, 10, -0.1, 10)
+    from oracle import peak_oracle
+    np.testing.assert_allclose(v, peak_oracle.peak_search_func(z["net0__phi"], 0.3, 10, -0.1, 10), rtol=1e-11)
+
+
+def test_peak_search_batched_vs_oracle(pkg):
+    from oracle import peak_oracle
+    z, sd = load_net_case("init_k10")
+    phis = z["phi_batch"]
+    opts = dict(xstep=0.02, ystep=0.02, iter=2)
+    r = pkg.alt_peak_search_batched(phis, 10, 10, opts, topl=3, pmax=8)       # pmax too small on purpose: grows
+    sep = lambda p, X, xb, Y, yb: peak_oracle.peak_search_separable(p, X[0], xb, Y[:, 0], yb)
+    for i in range(len(phis)):
+        exp = peak_oracle.alt_peak_search({"phi": phis[i], "xbase": 10, "ybase": 10}, opts, sep)
+        P = int(r["count"][i])
+        assert P == len(exp)
+        got = r["peaks"][i, :P].cpu().numpy()
+        assert np.array_equal(got[:, :2], exp[:, :2])
+        np.testing.assert_allclose(got[:, 2], exp[:, 2], rtol=1e-11)
+        np.testing.assert_array_equal(r["top"][i].cpu().numpy()[:, :2], peak_oracle.top_l(exp, 3)[:, :2])
+    # other dictionary sizes (config 4 of BASELINE.json: n in {64..256}, coarse grids 32^2..64^2)
+    rng = np.random.default_rng(0)
+    for nb, step in [(8, 1 / 32), (12, 1 / 45), (16, 1 / 64), (14, 1 / 32)]:
+        phi = (rng.normal(size=nb * nb) + 1j * rng.normal(size=nb * nb)).astype(np.complex64)
+        o = dict(xstep=step, ystep=step, iter=1)
+        got = pkg.alt_peak_search({"phi": phi, "xbase": nb, "ybase": nb}, o)
+        exp = peak_oracle.alt_peak_search({"phi": phi, "xbase": nb, "ybase": nb}, o, sep)
+        assert got.shape == exp.shape and np.array_equal(got[:, :2], exp[:, :2]), nb
+        np.testing.assert_allclose(got[:, 2], exp[:, 2], rtol=1e-10)
+
+
+def test_peak_plateau_and_degenerate_images(pkg):
+    # phi = 0 -> constant surface -> no maxima ; phi = e_0 -> constant 1 up to rounding (reference self-test shape)
+    out = pkg.alt_peak_search({"phi": np.zeros(100, dtype=np.complex64), "xbase": 10, "ybase": 10}, dict(iter=1))
+    assert out.shape == (0, 3)
+    out = pkg.alt_peak_search({"phi": np.ones(1, dtype=np.complex128), "xbase": 1, "ybase": 1},
+                              dict(xstep=0.1, ystep=0.1))
+    assert out.shape == (0, 3)                                  # n=1: |phi|^2 everywhere, one big plateau touching the border
+
+
+def test_end_to_end_recovers_targets(pkg):
+    """Physical sanity on the classical path (main.py:95-120): the three strongest peaks sit on the true (tau,f)."""
+    from oracle import signals
+    y, b, s, truth = signals.generate(4, seed=123, snr_demod=30.0)
+    for i in range(4):
+        phi, _ = pkg.admm_for_us(y[i].astype(np.complex128), b[i].astype(np.complex128), 10, 10, 1.0, float(s[i]))
+        pk = pkg.alt_peak_search({"phi": phi, "xbase": 10, "ybase": 10}, dict(xstep=0.01, ystep=0.01, iter=3))
+        top = sorted(pk, key=lambda p: p[2], reverse=True)[:1]
+        amp = np.abs(truth["C"][i])
+        j = int(np.argmax(amp))
+        assert abs(top[0][0] - truth["tau"][i][j]) < 0.05 and abs(top[0][1] - truth["f"][i][j]) < 0.05

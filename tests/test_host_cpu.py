@@ -1,0 +1,230 @@
+"""CPU tests of the host side: the C ABI loads and exports every symbol of include/admmnet_b200.h (no
+compute without a GPU), parameter packing, API mirror, error behaviour, and the multi-rank orchestration
+(gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    from admmnet_b200 import _capi
+    if not os.path.exists(_capi.LIB_PATH):
+        g.build()
+    return _capi
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "admmnet_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(built.EXPORTS), declared ^ set(built.EXPORTS)
+    L = built.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.admmnet_version() >= 100
+
+
+def test_argument_errors_are_reported_not_crashed(built):
+    L = built.lib()
+    nb = C.c_size_t()
+    assert L.admmnet_forward_workspace_bytes(0, 0, 100, 10, 0, C.byref(nb)) < 0
+    assert b"positive" in L.admmnet_last_error()
+    assert L.admmnet_forward_workspace_bytes(4, 0, 200, 10, 0, C.byref(nb)) < 0       # n > 127
+    assert L.admmnet_forward_workspace_bytes(4, 0, 100, 10, 1000, C.byref(nb)) < 0    # rcap not a multiple of 1024
+    assert L.admmnet_forward_workspace_bytes(1024, 256, 100, 10, 0, C.byref(nb)) == 0 and nb.value > 0
+    small = nb.value
+    assert L.admmnet_forward_workspace_bytes(1024, 1024, 100, 10, 0, C.byref(nb)) == 0 and nb.value > small
+    assert L.admmnet_forward(None, None, None, 4, 4, 10, 10, 10, None, None, None, 0, 0, None) < 0
+    assert L.admm_classic_forward(None, None, 1, 4, 100, 1.0, 5, None, None) < 0
+    assert L.peak_search_full(None, 0, 1, 10, 10, None, 1, None, 1, 0., 1., .01, -.5, .5, .01, .1, 1, 8, None, None, 0,
+                              None, None, None, None) < 0
+    assert L.admmnet_eigh_workspace_bytes(1, 300, 0, C.byref(nb)) < 0
+
+
+def test_param_packing_matches_layout(built):
+    from admmnet_b200 import params
+    from tests.helpers import load_net_case
+    import torch.nn.functional as F
+    z, sd = load_net_case("pert_k10")
+    P = params.pack_state_dict(sd, 100, 10)
+    assert P.shape == (10, built.lib().admmnet_param_stride(100)) == (10, params.param_stride(100))
+    k = 4
+    assert P[k, params.P_RHO_PHI] == F.softplus(sd[f"phiLayers.{k}.rho"])
+    assert P[k, params.P_KNORM] == torch.tensor(k / 10.0)
+    lam = F.softplus(sd[f"gLayers.{k}.lambda_param"])
+    assert P[k, params.P_C0] == torch.tensor((1.0 / (lam ** 2 + 1e-8)).item())
+    W1 = sd[f"hLayers.{k}.correction_net.0.weight"]
+    assert torch.equal(P[k, params.P_HW1T:params.P_HW1T + 6400].reshape(100, 64), W1.t())
+    W2 = sd[f"hLayers.{k}.correction_net.2.weight"]
+    assert torch.equal(P[k, params.P_HW1T + 6400:params.P_HW1T + 12800].reshape(64, 100), W2.t())
+    assert torch.equal(P[k, params.P_ZU1:params.P_ZU1 + 96].reshape(32, 3), sd[f"zLayers.{k}.residual_scale_net.0.weight"])
+
+
+def test_module_mirror_state_dict_and_seeded_init(built):
+    """Same keys, shapes and (same seed) same initial values as the reference module."""
+    import admm_net
+    from tests.helpers import load_net_case
+    z, sd = load_net_case("init_k10")
+    torch.manual_seed(0)
+    net = admm_net.PhiEstADMMNet(10, 10, 3, 10)
+    mine = net.state_dict()
+    assert list(mine.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(mine[k], sd[k]), k
+    assert sum(v.numel() for v in mine.values()) == 132230
+    net.load_state_dict(load_net_case("pert_k10")[1])                # reference checkpoints load
+    groups = [n for n, _ in net.named_parameters() if any(s in n for s in ("phiLayers", "hLayers", "gLayers", "zLayers"))]
+    assert len(groups) == len(list(net.parameters()))                # trainPhi.py:106-111 grouping still matches
+
+
+def test_product_path_has_no_cpu_fallback(built):
+    import admm_net
+    import admm
+    from utils import peakSearchUtils
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    net = admm_net.PhiEstADMMNet(10, 10, 3, 2)
+    with pytest.raises(built.AdmmnetError):
+        net(torch.ones(1, 100, dtype=torch.complex64), torch.ones(1, 100, dtype=torch.complex64), torch.ones(1))
+    with pytest.raises(built.AdmmnetError):
+        admm.admm_for_us(np.ones(100, complex), np.ones(100, complex), 10, 10, 1.0, 1.0)
+    with pytest.raises(built.AdmmnetError):
+        peakSearchUtils.alt_peak_search({"phi": np.ones(100, complex), "xbase": 10, "ybase": 10})
+    # ... and nothing under the package imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "admm-net_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(root, f)).read(), f
+
+
+def test_iteration_count_rule(built):
+    from admmnet_b200.admm import executed_iterations
+    assert executed_iterations(dict(max_iter=100)) == 5            # main.py:88-95 -> 5 (results/time/time.txt regime)
+    assert executed_iterations(None) == 5
+    assert executed_iterations(dict(max_iter=3)) == 3
+    assert executed_iterations(dict(max_iter=50), use_min_iter=False) == 2
+    assert executed_iterations(None, True, 7) == 7
+    assert executed_iterations(None, True, 1) == 2
+
+
+def test_coarse_axes_follow_reference_quirk(built):
+    from admmnet_b200.peaksearch import DEFAULT_OPTS, coarse_axes
+    ax, ay = coarse_axes({**DEFAULT_OPTS})
+    assert len(ax) == 99 and len(ay) == 99
+    ax, ay = coarse_axes({**DEFAULT_OPTS, "xstep": 0.04, "ystep": 0.02})
+    assert len(ay) == len(np.arange(-0.5, 0.5 - 0.04, 0.02))        # peakSearchUtils.py:106 uses xstep
+
+
+def test_shard_range():
+    from admmnet_b200.sharding import shard_range
+    for B, W in [(10, 3), (8, 8), (5, 8), (1048576, 8)]:
+        spans = [shard_range(B, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+# ------------------------------------------------------------------ world_size 2, gloo
+class _OracleEngine:
+    """Stand-in for sharding.CudaEngine built on the CPU oracle: same interface, lets the all-reduce
+    orchestration of run_layers be checked without a GPU."""
+
+    def __init__(self, sd, y, b, s, K):
+        from oracle import net_oracle
+        self.no, self.sd, self.y, self.b, self.s, self.K = net_oracle, sd, y, b, s, K
+        B = y.shape[0]
+        self.G = torch.zeros(B, 101, 101)
+        self.Z = torch.zeros(B, 101, 101)
+        self.rs = torch.zeros(K, dtype=torch.float64)
+        self.pending = None
+
+    def count(self):
+        return self.y.shape[0]
+
+    def _apply_pending(self):
+        if self.pending is not None:
+            phi, h, G, k, mean = self.pending
+            p = self.no.layer_params(self.sd, k)
+            self.Z, _, _ = self.no.z_update(phi, h, G, self.Z, k, p["z"], mean_r=mean)
+            self.pending = None
+
+    def layer(self, k):
+        self._apply_pending()
+        p = self.no.layer_params(self.sd, k)
+        phi = self.no.phi_update(self.y, self.b, self.G, self.Z, p["phi"]["rho"])
+        h = self.no.h_update(self.G, self.Z, self.s, 100, p["h"])
+        G, _, _, _ = self.no.g_update(phi, h, self.Z, p["g"])
+        _, r, _ = self.no.z_update(phi, h, G, self.Z, k, p["z"])
+        self.G = G
+        self.rs[k] = r.double().sum()
+        self.cur = (phi, h, G, k)
+
+    def rsum(self, k):
+        return self.rs[k:k + 1]
+
+    def set_mean(self, k, count):
+        self.pending = self.cur + (torch.tensor(float(self.rs[k] / count), dtype=torch.float32),)
+
+    def final(self):
+        self._apply_pending()
+        p = self.no.layer_params(self.sd, self.K - 1)
+        return self.no.phi_update(self.y, self.b, self.G, self.Z, p["phi"]["rho"])
+
+
+def _worker(rank, world, port, tag, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from admmnet_b200.sharding import run_layers, shard_range
+    from tests.helpers import load_net_case
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    z, sd = load_net_case(tag)
+    K = int(z["K"])
+    y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
+    lo, hi = shard_range(y.shape[0], rank, world)
+    out = {}
+    for scope in ("global", "shard"):
+        eng = _OracleEngine(sd, y[lo:hi], b[lo:hi], s[lo:hi], K)
+        out[scope] = run_layers(eng, K, scope).numpy()
+    q.put((rank, lo, hi, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_norm_scope_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    from oracle import net_oracle
+    from tests.helpers import load_net_case, rel_err
+    tag = "pert_k5"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, tag, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    z, sd = load_net_case(tag)
+    y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
+    phi_g = np.concatenate([r[3]["global"] for r in res])
+    # 'global': two ranks reproduce the reference's whole-batch result
+    assert rel_err(phi_g, z["phi_batch"]).max() < 5e-5
+    # 'shard': each rank equals the oracle run on its shard alone, and differs from the whole-batch result
+    for rank, lo, hi, out in res:
+        ref = net_oracle.forward(sd, y[lo:hi], b[lo:hi], s[lo:hi], 10, 10, int(z["K"])).numpy()
+        assert rel_err(out["shard"], ref).max() < 5e-5
+    assert rel_err(np.concatenate([r[3]["shard"] for r in res]), z["phi_batch"]).max() > 1e-4
