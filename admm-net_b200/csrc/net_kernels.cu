@@ -400,16 +400,28 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
             bool early = false;
             for (int i = m - 1; i >= l; --i) {
                 const double f = s * E_(i), bb = c * E_(i);
-                r = sqrt(f * f + g * g);
-                E_(i + 1) = r;
-                if (r == 0.0) {
+                const double h2 = f * f + g * g;
+                if (h2 == 0.0) {
+                    E_(i + 1) = 0.0;
                     D_(i + 1) -= p;
                     E_(m) = 0.0;
                     early = true;
                     break;
                 }
-                s = f / r;
-                c = g / r;
+                // 1/sqrt(h2): fp32 seed + two fp64 Newton steps (1e-7 -> 1e-14 -> 1e-28) instead of
+                // one sqrt and two divisions on the serial chain
+                double rinv;
+                if (h2 > 1e-30 && h2 < 1e30) {
+                    rinv = (double)rsqrtf((float)h2);
+                    rinv = rinv * (1.5 - 0.5 * h2 * rinv * rinv);
+                    rinv = rinv * (1.5 - 0.5 * h2 * rinv * rinv);
+                } else {
+                    rinv = 1.0 / sqrt(h2);
+                }
+                r = h2 * rinv;
+                E_(i + 1) = r;
+                s = f * rinv;
+                c = g * rinv;
                 g = D_(i + 1) - p;
                 r = (D_(i) - g) * s + 2.0 * c * bb;
                 p = s * r;
@@ -443,8 +455,10 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
 // k_rot: Z = I * (product of the recorded plane rotations).  One CTA per signal, thread = row of Z.
 // The rotation stream is staged through shared memory in double-buffered cp.async chunks.
 // =====================================================================================
-#define ROT_THREADS 128
-#define ROT_CHUNK 1024   // float2 entries per stage (8 KB)
+#define ROT_THREADS 32
+#define ROT_CHUNK 1024   // granularity of rcap (entries)
+#define ROT_STAGE 512    // float2 entries per cp.async stage (4 KB)
+#define ROT_ROWS 4       // rows per lane: lane, lane+32, lane+64, lane+96  (d <= 128)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -454,65 +468,113 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// One WARP per signal (CTA = 1 warp, ~45 KB of shared memory -> 5 CTAs per SM); each lane owns 4 rows of Z
+// so that one broadcast load of (c,s) feeds four independent rotation chains.
 __global__ void __launch_bounds__(ROT_THREADS)
 k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* stage = reinterpret_cast<float2*>(smem_raw);                  // [2][ROT_CHUNK]
-    float* z = reinterpret_cast<float*>(stage + 2 * ROT_CHUNK);           // [d][ldz]
+    float2* stage = reinterpret_cast<float2*>(smem_raw);                  // [2][ROT_STAGE]
+    float* z = reinterpret_cast<float*>(stage + 2 * ROT_STAGE);           // [d][ldz]
     const int ldz = d | 1;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     const int sig = blockIdx.x;
     const float2* src = rot + (size_t)sig * rcap;
     const int total = nrot[sig];
-    for (int idx = tid; idx < d * ldz; idx += ROT_THREADS) z[idx] = 0.f;
-    __syncthreads();
-    if (tid < d) z[tid * ldz + tid] = 1.f;
-    const int nchunks = (total + ROT_CHUNK - 1) / ROT_CHUNK;
+    for (int idx = lane; idx < d * ldz; idx += 32) z[idx] = 0.f;
+    __syncwarp();
+    for (int r = lane; r < d; r += 32) z[r * ldz + r] = 1.f;
+    const int nchunks = (total + ROT_STAGE - 1) / ROT_STAGE;
     auto issue = [&](int ch) {
-        const float2* g = src + (size_t)ch * ROT_CHUNK;
-        float2* sdst = stage + (ch & 1) * ROT_CHUNK;
-        // whole chunks are always readable: rcap is a multiple of ROT_CHUNK (checked on the host)
-        for (int q = tid; q < ROT_CHUNK / 2; q += ROT_THREADS) cp_async16(sdst + 2 * q, g + 2 * q);
+        const float2* g = src + (size_t)ch * ROT_STAGE;
+        float2* sdst = stage + (ch & 1) * ROT_STAGE;
+        // whole stages are always readable: rcap is a multiple of ROT_CHUNK (checked on the host)
+#pragma unroll
+        for (int q = lane; q < ROT_STAGE / 2; q += 32) cp_async16(sdst + 2 * q, g + 2 * q);
         cp_async_commit();
     };
     if (nchunks > 0) issue(0);
-    // parser state (identical in every thread; rows differ only in data)
+    float* zr[ROT_ROWS];
+    bool act[ROT_ROWS];
+    float carry[ROT_ROWS];
+#pragma unroll
+    for (int g = 0; g < ROT_ROWS; ++g) {
+        const int r = lane + 32 * g;
+        act[g] = r < d;
+        zr[g] = z + (size_t)(act[g] ? r : 0) * ldz;
+        carry[g] = 0.f;
+    }
     int remaining = 0, col = 0;
-    float carry = 0.f;
     bool done = false;
-    float* zr = z + (size_t)tid * ldz;
-    const bool active = tid < d;
     for (int ch = 0; ch < nchunks; ++ch) {
         if (ch + 1 < nchunks) { issue(ch + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
-        const float2* sbuf = stage + (ch & 1) * ROT_CHUNK;
-        const int cnt_here = min(ROT_CHUNK, total - ch * ROT_CHUNK);
-        if (!done) {
-            for (int q = 0; q < cnt_here; ++q) {
-                const float2 e = sbuf[q];
-                if (remaining == 0) {
-                    const int m = __float_as_int(e.x);
-                    if (m < 0) { done = true; break; }
-                    remaining = __float_as_int(e.y);
-                    col = m;                       // carry holds z[col]
-                    if (active) carry = zr[col];
-                    if (remaining == 0 && active) zr[col] = carry;
-                } else {
-                    if (active) {
-                        const float zi = zr[col - 1];
-                        zr[col] = e.y * zi + e.x * carry;     // z[i+1] = s*z[i] + c*f
-                        carry = e.x * zi - e.y * carry;       // z[i]   = c*z[i] - s*f
+        __syncwarp();
+        const float2* sbuf = stage + (ch & 1) * ROT_STAGE;
+        const int cnt_here = min(ROT_STAGE, total - ch * ROT_STAGE);
+        int q = 0;
+        while (!done && q < cnt_here) {
+            if (remaining == 0) {
+                const float2 e = sbuf[q++];
+                const int m = __float_as_int(e.x);
+                if (m < 0) { done = true; break; }
+                remaining = __float_as_int(e.y);
+                col = m;                                    // carry holds z[.][col]
+#pragma unroll
+                for (int g = 0; g < ROT_ROWS; ++g) carry[g] = act[g] ? zr[g][col] : 0.f;
+                continue;
+            }
+            const int run = min(remaining, cnt_here - q);
+            int t = 0;
+            // batches of 4 rotations: all loads first (independent of the carry chain), then the
+            // four dependent rotations per row, then the stores
+            for (; t + 4 <= run; t += 4) {
+                const float2 e0 = sbuf[q + t], e1 = sbuf[q + t + 1], e2 = sbuf[q + t + 2], e3 = sbuf[q + t + 3];
+                const int ci = col - 1 - t;
+                float z0[ROT_ROWS], z1[ROT_ROWS], z2[ROT_ROWS], z3[ROT_ROWS];
+#pragma unroll
+                for (int g = 0; g < ROT_ROWS; ++g) {
+                    const float* zp = zr[g] + ci;
+                    z0[g] = zp[0]; z1[g] = zp[-1]; z2[g] = zp[-2]; z3[g] = zp[-3];
+                }
+#pragma unroll
+                for (int g = 0; g < ROT_ROWS; ++g) {
+                    float cy = carry[g];
+                    const float o0 = e0.y * z0[g] + e0.x * cy; cy = e0.x * z0[g] - e0.y * cy;
+                    const float o1 = e1.y * z1[g] + e1.x * cy; cy = e1.x * z1[g] - e1.y * cy;
+                    const float o2 = e2.y * z2[g] + e2.x * cy; cy = e2.x * z2[g] - e2.y * cy;
+                    const float o3 = e3.y * z3[g] + e3.x * cy; cy = e3.x * z3[g] - e3.y * cy;
+                    carry[g] = cy;
+                    if (act[g]) {
+                        float* zp = zr[g] + ci;
+                        zp[1] = o0; zp[0] = o1; zp[-1] = o2; zp[-2] = o3;
                     }
-                    --col;
-                    if (--remaining == 0 && active) zr[col] = carry;
                 }
             }
+            for (; t < run; ++t) {
+                const float2 e = sbuf[q + t];               // (c, s)
+                const int ci = col - 1 - t;
+#pragma unroll
+                for (int g = 0; g < ROT_ROWS; ++g) {
+                    if (act[g]) {
+                        const float zi = zr[g][ci];
+                        zr[g][ci + 1] = e.y * zi + e.x * carry[g];      // z[i+1] = s*z[i] + c*f
+                        carry[g] = e.x * zi - e.y * carry[g];           // z[i]   = c*z[i] - s*f
+                    }
+                }
+            }
+            q += run;
+            col -= run;
+            remaining -= run;
+            if (remaining == 0) {
+#pragma unroll
+                for (int g = 0; g < ROT_ROWS; ++g)
+                    if (act[g]) zr[g][col] = carry[g];
+            }
         }
-        __syncthreads();   // stage buffer (ch&1) is refilled by issue(ch+2)
+        __syncwarp();   // stage buffer (ch&1) is refilled by issue(ch+2)
     }
-    __syncthreads();
+    __syncwarp();
     float* outz = Zr + (size_t)sig * d * d;
-    for (int idx = tid; idx < d * d; idx += ROT_THREADS) outz[idx] = z[(idx / d) * ldz + (idx % d)];
+    for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldz + (idx % d)];
 }
 
 // =====================================================================================
