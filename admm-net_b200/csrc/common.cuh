@@ -102,8 +102,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 // packed lower-triangular (row-major) index, j <= i
 __host__ __device__ __forceinline__ int pk(int i, int j) { return (i * (i + 1)) / 2 + j; }
-// Householder-vector store: column k holds rows k+2..d-1 (v[k+1] == 1 implicit), columns concatenated
-__host__ __device__ __forceinline__ int voff(int k, int d) { return k * (d - 2) - (k * (k - 1)) / 2; }
+// Householder-vector store: column k holds rows k+1..d-1 (v[k+1] == 1 stored explicitly), columns concatenated
+__host__ __device__ __forceinline__ int voff(int k, int d) { return k * (d - 1) - (k * (k - 1)) / 2; }
 
 // adaptive dual step alpha (admm_net.py:443-474) for one signal
 __device__ __forceinline__ float z_alpha(const float* __restrict__ P, float r, float mean_r) {

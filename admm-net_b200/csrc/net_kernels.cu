@@ -137,9 +137,10 @@ __device__ void export_tridiag(const float2* __restrict__ A, int d, int ld, cons
                                const float* ee, float2* __restrict__ Vg, float2* __restrict__ taug,
                                float* __restrict__ dT, float* __restrict__ eT, int B, int sig) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    for (int k = wid; k < d - 2; k += nw) {
+    for (int k = wid; k < d - 1; k += nw) {
         const int off = voff(k, d);
-        for (int i = k + 2 + lane; i < d; i += 32) Vg[off + i - (k + 2)] = A[i + (size_t)k * ld];
+        for (int i = k + 1 + lane; i < d; i += 32)
+            Vg[off + i - (k + 1)] = (i == k + 1) ? make_float2(1.f, 0.f) : A[i + (size_t)k * ld];
     }
     for (int i = tid; i < d; i += blockDim.x) {
         taug[i] = i < d - 1 ? tau_s[i] : make_float2(0.f, 0.f);
@@ -596,7 +597,7 @@ struct TailArgs {
     int B, n, d, ldu, with_c;  // with_c=0: plain f(A) for the debug entry (no residual)
 };
 __host__ __device__ inline size_t tail_smem_bytes(int d, int ldu) {
-    const size_t nv = (size_t)(d - 1) * (d - 2) / 2;
+    const size_t nv = (size_t)d * (d - 1) / 2;
     return ((size_t)d * ldu + nv + 2 + 128 /*tau*/ + 128 /*phi*/) * sizeof(float2) + (128 + 128 + 96) * sizeof(float);
 }
 
@@ -604,7 +605,7 @@ template <int NR, int NT>
 __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, d = a.d, ldu = a.ldu;
-    const int nv = (d - 1) * (d - 2) / 2;
+    const int nv = d * (d - 1) / 2;
     float2* U = reinterpret_cast<float2*>(smem_raw);          // [d][ldu] column-major (also Z staging)
     float2* Vs = U + (size_t)d * ldu;                         // reflectors
     float2* taus = Vs + ((nv + 1) & ~1);
@@ -649,38 +650,40 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
         M1[j] = make_float2((r < d && c1 < d) ? Zs[r * d + c1] : 0.f, 0.f);
     }
     __syncthreads();   // Z staging area is dead from here on (becomes U)
-    for (int k = d - 2; k >= 0; --k) {
-        const float2 tk = taus[k];
-        if (tk.x == 0.f && tk.y == 0.f) continue;
-        const float2* vk = Vs + voff(k, d) - (k + 2);     // vk[r] valid for r >= k+2
-        float2 vv[NR];
-        float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+    // Reflector k touches rows r > k.  Rows are held as r = s8 + 8j, so for the 8 reflectors with
+    // (k+1)/8 == jm only the row slots j >= jm take part: slot jm under a per-lane predicate, slots > jm
+    // unconditionally (compile-time bounds after unrolling jm -> no per-slot branches in the hot loop).
 #pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            vv[j] = make_float2(0.f, 0.f);
-            if (8 * j + 7 >= k + 1) {
+    for (int jm = NR - 1; jm >= 0; --jm) {
+        const int khi = min(8 * jm + 6, d - 2), klo = max(8 * jm - 1, 0);
+        for (int k = khi; k >= klo; --k) {
+            const float2 tk = taus[k];
+            if (tk.x == 0.f && tk.y == 0.f) continue;
+            const int vbase = voff(k, d) - (k + 1);           // Vs[vbase + r] valid for r >= k+1
+            float2 vv[NR];
+            float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = jm; j < NR; ++j) {
                 const int r = s8 + 8 * j;
-                if (r > k && r < d) {
-                    const float2 v = (r == k + 1) ? make_float2(1.f, 0.f) : vk[r];
-                    vv[j] = v;
-                    d0.x += v.x * M0[j].x + v.y * M0[j].y;
-                    d0.y += v.x * M0[j].y - v.y * M0[j].x;
-                    d1.x += v.x * M1[j].x + v.y * M1[j].y;
-                    d1.y += v.x * M1[j].y - v.y * M1[j].x;
-                }
+                const bool on = (j == jm ? r > k : true) && (r < d);
+                float2 v = make_float2(0.f, 0.f);
+                if (on) v = Vs[vbase + r];
+                vv[j] = v;
+                d0.x += v.x * M0[j].x + v.y * M0[j].y;
+                d0.y += v.x * M0[j].y - v.y * M0[j].x;
+                d1.x += v.x * M1[j].x + v.y * M1[j].y;
+                d1.y += v.x * M1[j].y - v.y * M1[j].x;
             }
-        }
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            d0.x += __shfl_xor_sync(0xffffffffu, d0.x, o);
-            d0.y += __shfl_xor_sync(0xffffffffu, d0.y, o);
-            d1.x += __shfl_xor_sync(0xffffffffu, d1.x, o);
-            d1.y += __shfl_xor_sync(0xffffffffu, d1.y, o);
-        }
-        const float2 t0 = cmul(tk, d0), t1 = cmul(tk, d1);
+            for (int o = 1; o < 8; o <<= 1) {
+                d0.x += __shfl_xor_sync(0xffffffffu, d0.x, o);
+                d0.y += __shfl_xor_sync(0xffffffffu, d0.y, o);
+                d1.x += __shfl_xor_sync(0xffffffffu, d1.x, o);
+                d1.y += __shfl_xor_sync(0xffffffffu, d1.y, o);
+            }
+            const float2 t0 = cmul(tk, d0), t1 = cmul(tk, d1);
 #pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            if (8 * j + 7 >= k + 1) {
+            for (int j = jm; j < NR; ++j) {
                 const float2 v = vv[j];
                 M0[j].x -= t0.x * v.x - t0.y * v.y;
                 M0[j].y -= t0.x * v.y + t0.y * v.x;
