@@ -26,109 +26,152 @@ namespace admmnet {
 // 256 threads: (r = tid & 127, half = tid >> 7).
 // =====================================================================================
 struct TriScratch {
-    float2* v;      // [128]
-    float2* w;      // [128]
-    float2* part;   // [256]
-    float* red;     // [96]
-    float2* scal;   // [4]: tau, scale, (beta,0)
+    float4* vw;     // [128] pending rank-2 update, indexed by global row: (v.x, v.y, w.x, w.y)
+    float2* vn;     // [128] reflector being formed, indexed by global row
+    float2* part;   // [8][128] partial mat-vec sums
+    float* red;     // [2][32] block-reduction scratch (double buffered)
+    float2* scal;   // [4]
 };
+
+// One fused sweep over the trailing block (rows/cols k+1..d-1):
+//     A <- A - v w^H - w v^H   (pending update of the previous step)     and     part[q][r] = sum_c A[r][c] vn[c]
+// NROWS rows per thread (r, r+RSTRIDE); column groups q = tid / RSTRIDE, c = q, q+NQ, ...
+template <int NROWS, int RSTRIDE>
+__device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, int k, int m, const TriScratch& S) {
+    constexpr int NQ = 256 / RSTRIDE;
+    const int tid = threadIdx.x;
+    const int rr = tid & (RSTRIDE - 1), q = tid / RSTRIDE;
+    const int g0 = k + 1;                       // global index of local row/col 0
+    float2 vo[NROWS], wo[NROWS], acc[NROWS];
+    bool on[NROWS];
+#pragma unroll
+    for (int i = 0; i < NROWS; ++i) {
+        const int rl = rr + i * RSTRIDE;
+        on[i] = rl < m;
+        const float4 t = S.vw[g0 + (on[i] ? rl : 0)];
+        vo[i] = make_float2(t.x, t.y);
+        wo[i] = make_float2(t.z, t.w);
+        acc[i] = make_float2(0.f, 0.f);
+    }
+    if (on[0]) {
+        float2* a0 = A + (g0 + rr) + (size_t)g0 * ld;
+#pragma unroll 2
+        for (int c = q; c < m; c += NQ) {
+            const float4 t = S.vw[g0 + c];
+            const float2 vn = S.vn[g0 + c];
+#pragma unroll
+            for (int i = 0; i < NROWS; ++i) {
+                if (i == 0 || on[i]) {
+                    float2* ap = a0 + i * RSTRIDE + (size_t)c * ld;
+                    float2 x = *ap;
+                    // x -= v_r conj(w_c) + w_r conj(v_c)
+                    x.x -= vo[i].x * t.z + vo[i].y * t.w + wo[i].x * t.x + wo[i].y * t.y;
+                    x.y -= vo[i].y * t.z - vo[i].x * t.w + wo[i].y * t.x - wo[i].x * t.y;
+                    *ap = x;
+                    acc[i].x += x.x * vn.x - x.y * vn.y;
+                    acc[i].y += x.x * vn.y + x.y * vn.x;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NROWS; ++i) {
+        const int rl = rr + i * RSTRIDE;
+        if (rl < 128) S.part[q * 128 + rl] = acc[i];
+    }
+}
 
 __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S, float2* tau_out, float* dd,
                              float* ee) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int r = tid & 127, half = tid >> 7;
+    if (tid < 128) S.vw[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
     for (int k = 0; k < d - 1; ++k) {
         const int m = d - k - 1;            // trailing size, rows/cols k+1..d-1
-        float2* colk = A + (size_t)k * ld;  // column k
-        // ---- S1: reflector scalars (warp 0)
-        if (wid == 0) {
-            float ss = 0.f;
-            for (int i = k + 2 + lane; i < d; i += 32) {
-                float2 x = colk[i];
-                ss += x.x * x.x + x.y * x.y;
-            }
-            ss = warp_sum(ss);
-            if (lane == 0) {
-                const float2 alpha = colk[k + 1];
-                float2 tau, scale;
-                float beta;
-                if (ss == 0.f && alpha.y == 0.f) {
-                    tau = make_float2(0.f, 0.f);
-                    scale = make_float2(0.f, 0.f);
-                    beta = alpha.x;
-                } else {
-                    beta = -copysignf(sqrtf(alpha.x * alpha.x + alpha.y * alpha.y + ss), alpha.x);
-                    tau = make_float2((beta - alpha.x) / beta, -alpha.y / beta);
-                    scale = cdiv(make_float2(1.f, 0.f), make_float2(alpha.x - beta, alpha.y));
-                }
-                S.scal[0] = tau;
-                S.scal[1] = scale;
-                tau_out[k] = tau;
-                ee[k] = beta;
-                dd[k] = A[k + (size_t)k * ld].x;
-            }
+        float* red = S.red + (k & 1) * 32;
+        // ---- phase A: column k with the pending update applied; its norm
+        float2 a = make_float2(0.f, 0.f);
+        float ss = 0.f;
+        if (tid <= m) {
+            const int r = k + tid;
+            a = A[r + (size_t)k * ld];
+            const float4 tr = S.vw[r], tk = S.vw[k];
+            a.x -= tr.x * tk.z + tr.y * tk.w + tr.z * tk.x + tr.w * tk.y;
+            a.y -= tr.y * tk.z - tr.x * tk.w + tr.w * tk.x - tr.z * tk.y;
+            if (tid == 0) dd[k] = a.x;
+            if (tid == 1) S.scal[0] = a;
+            if (tid >= 2) ss = a.x * a.x + a.y * a.y;
         }
-        __syncthreads();
-        const float2 tau = S.scal[0];
-        if (tau.x != 0.f || tau.y != 0.f) {  // uniform branch (H_k == I otherwise)
-            const float2 scale = S.scal[1];
-            if (tid < m) {
-                float2 vi = make_float2(1.f, 0.f);
-                if (tid > 0) {
-                    vi = cmul(colk[k + 1 + tid], scale);
-                    colk[k + 1 + tid] = vi;
-                }
-                S.v[tid] = vi;
-            }
-            __syncthreads();
-            // ---- S2: p = A22 v (two interleaved column halves)
-            {
-                float2 acc = make_float2(0.f, 0.f);
-                if (r < m) {
-                    const float2* a = A + (k + 1 + r) + (size_t)(k + 1) * ld;
-#pragma unroll 4
-                    for (int c = half; c < m; c += 2) {
-                        const float2 x = a[(size_t)c * ld];
-                        const float2 vc = S.v[c];
-                        acc.x += x.x * vc.x - x.y * vc.y;
-                        acc.y += x.x * vc.y + x.y * vc.x;
-                    }
-                }
-                S.part[tid] = acc;
-            }
-            __syncthreads();
-            // ---- S3: p = tau*(..), dot = p^H v, w = p - (tau/2)(p^H v) v
-            float2 p = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
-            float dot[2] = {0.f, 0.f};
-            if (tid < m) {
-                p = cmul(tau, cadd(S.part[tid], S.part[tid + 128]));
-                vr = S.v[tid];
-                const float2 t = cconjmul(p, vr);
-                dot[0] = t.x;
-                dot[1] = t.y;
-            }
-            block_sum<2>(dot, S.red);
-            const float2 a2 = cmul(make_float2(-0.5f * tau.x, -0.5f * tau.y), make_float2(dot[0], dot[1]));
-            if (tid < m) S.w[tid] = cadd(p, cmul(a2, vr));
-            __syncthreads();
-            // ---- S4: A22 -= v w^H + w v^H
-            if (r < m) {
-                const float2 vrr = S.v[r], wrr = S.w[r];
-                float2* a = A + (k + 1 + r) + (size_t)(k + 1) * ld;
-#pragma unroll 4
-                for (int c = half; c < m; c += 2) {
-                    const float2 vc = S.v[c], wc = S.w[c];
-                    float2 x = a[(size_t)c * ld];
-                    // v_r conj(w_c) + w_r conj(v_c)
-                    x.x -= vrr.x * wc.x + vrr.y * wc.y + wrr.x * vc.x + wrr.y * vc.y;
-                    x.y -= vrr.y * wc.x - vrr.x * wc.y + wrr.y * vc.x - wrr.x * vc.y;
-                    a[(size_t)c * ld] = x;
-                }
-            }
+        ss = warp_sum(ss);
+        if (lane == 0) red[wid] = ss;
+        __syncthreads();                                           // (1)
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        const float2 alpha = S.scal[0];
+        float2 tau, scale;
+        float beta;
+        if (tot == 0.f && alpha.y == 0.f) {
+            tau = make_float2(0.f, 0.f);
+            scale = make_float2(0.f, 0.f);
+            beta = alpha.x;
+        } else {
+            beta = -copysignf(sqrtf(alpha.x * alpha.x + alpha.y * alpha.y + tot), alpha.x);
+            tau = make_float2((beta - alpha.x) / beta, -alpha.y / beta);
+            scale = cdiv(make_float2(1.f, 0.f), make_float2(alpha.x - beta, alpha.y));
         }
-        __syncthreads();
+        if (tid >= 1 && tid <= m) {
+            const int r = k + tid;
+            float2 vi = make_float2(1.f, 0.f);
+            if (tid >= 2) {
+                vi = cmul(a, scale);
+                A[r + (size_t)k * ld] = vi;                        // kept for the export of the reflectors
+            }
+            S.vn[r] = vi;
+        }
+        if (tid == 0) {
+            tau_out[k] = tau;
+            ee[k] = beta;
+        }
+        __syncthreads();                                           // (2)
+        // ---- phase B: fused pending update + mat-vec with the new reflector
+        if (m > 64) tri_fused_pass<2, 64>(A, ld, k, m, S);
+        else if (m > 32) tri_fused_pass<1, 64>(A, ld, k, m, S);
+        else tri_fused_pass<1, 32>(A, ld, k, m, S);
+        __syncthreads();                                           // (3)
+        // ---- phase C: p = tau * sum(partials); w = p - (tau/2)(p^H v) v
+        const int nq = m > 32 ? 4 : 8;
+        float2 p = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
+        float dx = 0.f, dy = 0.f;
+        if (tid < m) {
+            float2 sacc = make_float2(0.f, 0.f);
+            for (int qq = 0; qq < nq; ++qq) sacc = cadd(sacc, S.part[qq * 128 + tid]);
+            p = cmul(tau, sacc);
+            vr = S.vn[k + 1 + tid];
+            const float2 t = cconjmul(p, vr);
+            dx = t.x;
+            dy = t.y;
+        }
+        dx = warp_sum(dx);
+        dy = warp_sum(dy);
+        float* red2 = red + 8;
+        if (lane == 0) { red2[wid] = dx; red2[8 + wid] = dy; }
+        __syncthreads();                                           // (4)
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { sx += red2[w]; sy += red2[8 + w]; }
+        const float2 a2 = cmul(make_float2(-0.5f * tau.x, -0.5f * tau.y), make_float2(sx, sy));
+        if (tid < m) {
+            const float2 w = cadd(p, cmul(a2, vr));
+            S.vw[k + 1 + tid] = make_float4(vr.x, vr.y, w.x, w.y);
+        }
+        __syncthreads();                                           // (5)
     }
-    if (tid == 0) dd[d - 1] = A[(d - 1) + (size_t)(d - 1) * ld].x;
+    if (tid == 0) {
+        const int r = d - 1;
+        const float4 t = S.vw[r];
+        dd[r] = A[r + (size_t)r * ld].x - 2.f * (t.x * t.z + t.y * t.w);
+    }
     __syncthreads();
 }
 
@@ -166,7 +209,8 @@ struct HeadSmem {
     float* h;       // [n]
 };
 __host__ __device__ inline size_t head_smem_bytes(int d, int ld) {
-    size_t f2 = (size_t)d * ld + 128 + 128 + 256 + 4 + 128 /*tau*/ + 4 * 128 /*phi,gcol,zeta,phip*/;
+    size_t f2 = (size_t)d * ld + 1 /*align*/ + 256 /*vw*/ + 128 /*vn*/ + 1024 /*part*/ + 4 + 128 /*tau*/ +
+                4 * 128 /*phi,gcol,zeta,phip*/;
     size_t f1 = 96 + 128 + 128 /*dd,ee*/ + 128 /*hp*/ + 128 /*t*/ + 64 + 128 /*h*/;
     return f2 * sizeof(float2) + f1 * sizeof(float);
 }
@@ -174,9 +218,10 @@ __device__ inline HeadSmem carve_head(unsigned char* base, int d, int ld) {
     HeadSmem s;
     float2* p2 = reinterpret_cast<float2*>(base);
     s.A = p2; p2 += (size_t)d * ld;
-    s.S.v = p2; p2 += 128;
-    s.S.w = p2; p2 += 128;
-    s.S.part = p2; p2 += 256;
+    p2 += ((size_t)d * ld) & 1;                          // float4 alignment of vw
+    s.S.vw = reinterpret_cast<float4*>(p2); p2 += 256;
+    s.S.vn = p2; p2 += 128;
+    s.S.part = p2; p2 += 1024;
     s.S.scal = p2; p2 += 4;
     s.tau = p2; p2 += 128;
     s.phi = p2; p2 += 128;
