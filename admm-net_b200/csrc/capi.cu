@@ -149,7 +149,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(cudaGetLastError());
     }
     {
-        const size_t sm = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (d | 1) * sizeof(float);
+        const size_t sm = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (4 * ((d + 3) / 4)) * sizeof(float);
         CK(cudaFuncSetAttribute(k_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::ROT, st);
         k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr);

@@ -65,11 +65,13 @@ __device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, i
                     float2* ap = a0 + i * RSTRIDE + (size_t)c * ld;
                     float2 x = *ap;
                     // x -= v_r conj(w_c) + w_r conj(v_c)
-                    x.x -= vo[i].x * t.z + vo[i].y * t.w + wo[i].x * t.x + wo[i].y * t.y;
-                    x.y -= vo[i].y * t.z - vo[i].x * t.w + wo[i].y * t.x - wo[i].x * t.y;
+                    x.x = fmaf(-vo[i].x, t.z, x.x); x.x = fmaf(-vo[i].y, t.w, x.x);
+                    x.x = fmaf(-wo[i].x, t.x, x.x); x.x = fmaf(-wo[i].y, t.y, x.x);
+                    x.y = fmaf(-vo[i].y, t.z, x.y); x.y = fmaf(vo[i].x, t.w, x.y);
+                    x.y = fmaf(-wo[i].y, t.x, x.y); x.y = fmaf(wo[i].x, t.y, x.y);
                     *ap = x;
-                    acc[i].x += x.x * vn.x - x.y * vn.y;
-                    acc[i].y += x.x * vn.y + x.y * vn.x;
+                    acc[i].x = fmaf(x.x, vn.x, acc[i].x); acc[i].x = fmaf(-x.y, vn.y, acc[i].x);
+                    acc[i].y = fmaf(x.x, vn.y, acc[i].y); acc[i].y = fmaf(x.y, vn.x, acc[i].y);
                 }
             }
         }
@@ -504,7 +506,6 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
 #define ROT_THREADS 32
 #define ROT_CHUNK 1024   // granularity of rcap (entries)
 #define ROT_STAGE 512    // float2 entries per cp.async stage (4 KB)
-#define ROT_ROWS 4       // rows per lane: lane, lane+32, lane+64, lane+96  (d <= 128)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -514,21 +515,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// One WARP per signal (CTA = 1 warp, ~45 KB of shared memory -> 5 CTAs per SM); each lane owns 4 rows of Z
-// so that one broadcast load of (c,s) feeds four independent rotation chains.
+__device__ __forceinline__ void rot4(float4& out, float4& cy, const float4 zi, const float2 e) {
+    // z[i+1] = s*z[i] + c*f ;  z[i] = c*z[i] - s*f   (f = carry), four rows at once
+    out.x = fmaf(e.y, zi.x, e.x * cy.x); cy.x = fmaf(e.x, zi.x, -e.y * cy.x);
+    out.y = fmaf(e.y, zi.y, e.x * cy.y); cy.y = fmaf(e.x, zi.y, -e.y * cy.y);
+    out.z = fmaf(e.y, zi.z, e.x * cy.z); cy.z = fmaf(e.x, zi.z, -e.y * cy.z);
+    out.w = fmaf(e.y, zi.w, e.x * cy.w); cy.w = fmaf(e.x, zi.w, -e.y * cy.w);
+}
+
+// One WARP per signal (CTA = 1 warp, ~46 KB of shared memory -> 4-5 CTAs per SM).  Z is kept TRANSPOSED in
+// shared memory, zt[col][row] with ldr = 4*ceil(d/4) rows per column; lane l owns the four adjacent rows
+// 4l..4l+3, so one rotation is one 128-bit load, 16 FP ops and one 128-bit store per lane, and one
+// broadcast load of (c,s) feeds four independent chains.  Output: Z^T, i.e. Zt[c][r] row-major [d][d].
 __global__ void __launch_bounds__(ROT_THREADS)
-k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zr) {
+k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* stage = reinterpret_cast<float2*>(smem_raw);                  // [2][ROT_STAGE]
-    float* z = reinterpret_cast<float*>(stage + 2 * ROT_STAGE);           // [d][ldz]
-    const int ldz = d | 1;
+    float* z = reinterpret_cast<float*>(stage + 2 * ROT_STAGE);           // [d][ldr]
+    const int ldr = 4 * ((d + 3) / 4);
     const int lane = threadIdx.x;
     const int sig = blockIdx.x;
     const float2* src = rot + (size_t)sig * rcap;
     const int total = nrot[sig];
-    for (int idx = lane; idx < d * ldz; idx += 32) z[idx] = 0.f;
+    for (int idx = lane; idx < d * ldr; idx += 32) z[idx] = 0.f;
     __syncwarp();
-    for (int r = lane; r < d; r += 32) z[r * ldz + r] = 1.f;
+    for (int r = lane; r < d; r += 32) z[r * ldr + r] = 1.f;
     const int nchunks = (total + ROT_STAGE - 1) / ROT_STAGE;
     auto issue = [&](int ch) {
         const float2* g = src + (size_t)ch * ROT_STAGE;
@@ -539,16 +550,10 @@ k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, in
         cp_async_commit();
     };
     if (nchunks > 0) issue(0);
-    float* zr[ROT_ROWS];
-    bool act[ROT_ROWS];
-    float carry[ROT_ROWS];
-#pragma unroll
-    for (int g = 0; g < ROT_ROWS; ++g) {
-        const int r = lane + 32 * g;
-        act[g] = r < d;
-        zr[g] = z + (size_t)(act[g] ? r : 0) * ldz;
-        carry[g] = 0.f;
-    }
+    const bool act = 4 * lane < ldr;
+    float4* zq = reinterpret_cast<float4*>(z) + (act ? lane : 0);        // column c at zq[c * (ldr/4)]
+    const int lq = ldr / 4;
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
     int remaining = 0, col = 0;
     bool done = false;
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -564,63 +569,42 @@ k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, in
                 if (m < 0) { done = true; break; }
                 remaining = __float_as_int(e.y);
                 col = m;                                    // carry holds z[.][col]
-#pragma unroll
-                for (int g = 0; g < ROT_ROWS; ++g) carry[g] = act[g] ? zr[g][col] : 0.f;
+                carry = zq[col * lq];
                 continue;
             }
             const int run = min(remaining, cnt_here - q);
             int t = 0;
-            // batches of 4 rotations: all loads first (independent of the carry chain), then the
-            // four dependent rotations per row, then the stores
+            // batches of 4 rotations: loads first (independent of the carry chain), then the four
+            // dependent rotations, then the stores
             for (; t + 4 <= run; t += 4) {
                 const float2 e0 = sbuf[q + t], e1 = sbuf[q + t + 1], e2 = sbuf[q + t + 2], e3 = sbuf[q + t + 3];
-                const int ci = col - 1 - t;
-                float z0[ROT_ROWS], z1[ROT_ROWS], z2[ROT_ROWS], z3[ROT_ROWS];
-#pragma unroll
-                for (int g = 0; g < ROT_ROWS; ++g) {
-                    const float* zp = zr[g] + ci;
-                    z0[g] = zp[0]; z1[g] = zp[-1]; z2[g] = zp[-2]; z3[g] = zp[-3];
-                }
-#pragma unroll
-                for (int g = 0; g < ROT_ROWS; ++g) {
-                    float cy = carry[g];
-                    const float o0 = e0.y * z0[g] + e0.x * cy; cy = e0.x * z0[g] - e0.y * cy;
-                    const float o1 = e1.y * z1[g] + e1.x * cy; cy = e1.x * z1[g] - e1.y * cy;
-                    const float o2 = e2.y * z2[g] + e2.x * cy; cy = e2.x * z2[g] - e2.y * cy;
-                    const float o3 = e3.y * z3[g] + e3.x * cy; cy = e3.x * z3[g] - e3.y * cy;
-                    carry[g] = cy;
-                    if (act[g]) {
-                        float* zp = zr[g] + ci;
-                        zp[1] = o0; zp[0] = o1; zp[-1] = o2; zp[-2] = o3;
-                    }
-                }
+                float4* zp = zq + (col - 1 - t) * lq;       // column ci = col-1-t
+                const float4 z0 = zp[0], z1 = zp[-lq], z2 = zp[-2 * lq], z3 = zp[-3 * lq];
+                float4 o0, o1, o2, o3;
+                rot4(o0, carry, z0, e0);
+                rot4(o1, carry, z1, e1);
+                rot4(o2, carry, z2, e2);
+                rot4(o3, carry, z3, e3);
+                if (act) { zp[lq] = o0; zp[0] = o1; zp[-lq] = o2; zp[-2 * lq] = o3; }
             }
             for (; t < run; ++t) {
                 const float2 e = sbuf[q + t];               // (c, s)
-                const int ci = col - 1 - t;
-#pragma unroll
-                for (int g = 0; g < ROT_ROWS; ++g) {
-                    if (act[g]) {
-                        const float zi = zr[g][ci];
-                        zr[g][ci + 1] = e.y * zi + e.x * carry[g];      // z[i+1] = s*z[i] + c*f
-                        carry[g] = e.x * zi - e.y * carry[g];           // z[i]   = c*z[i] - s*f
-                    }
-                }
+                float4* zp = zq + (col - 1 - t) * lq;
+                const float4 zi = zp[0];
+                float4 o;
+                rot4(o, carry, zi, e);
+                if (act) zp[lq] = o;
             }
             q += run;
             col -= run;
             remaining -= run;
-            if (remaining == 0) {
-#pragma unroll
-                for (int g = 0; g < ROT_ROWS; ++g)
-                    if (act[g]) zr[g][col] = carry[g];
-            }
+            if (remaining == 0 && act) zq[col * lq] = carry;
         }
         __syncwarp();   // stage buffer (ch&1) is refilled by issue(ch+2)
     }
     __syncwarp();
-    float* outz = Zr + (size_t)sig * d * d;
-    for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldz + (idx % d)];
+    float* outz = Zt + (size_t)sig * d * d;
+    for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldr + (idx % d)];
 }
 
 // =====================================================================================
@@ -629,7 +613,7 @@ k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, in
 // rows s+8j kept in registers for all d-1 reflectors -> no block barrier inside that phase.
 // =====================================================================================
 struct TailArgs {
-    const float* Zr;        // [B][d][d]
+    const float* Zr;        // [B][d][d]  Z transposed: Zr[c][r]
     float2* GV;             // [B][npk]: reflectors on entry, G packed lower on exit
     const float2* tau;      // [B][d]
     const float* lam;       // [B][d]
@@ -691,8 +675,8 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
         const int r = s8 + 8 * j;
-        M0[j] = make_float2((r < d && c0 < d) ? Zs[r * d + c0] : 0.f, 0.f);
-        M1[j] = make_float2((r < d && c1 < d) ? Zs[r * d + c1] : 0.f, 0.f);
+        M0[j] = make_float2((r < d && c0 < d) ? Zs[c0 * d + r] : 0.f, 0.f);
+        M1[j] = make_float2((r < d && c1 < d) ? Zs[c1 * d + r] : 0.f, 0.f);
     }
     __syncthreads();   // Z staging area is dead from here on (becomes U)
     // Reflector k touches rows r > k.  Rows are held as r = s8 + 8j, so for the 8 reflectors with
@@ -714,10 +698,10 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
                 float2 v = make_float2(0.f, 0.f);
                 if (on) v = Vs[vbase + r];
                 vv[j] = v;
-                d0.x += v.x * M0[j].x + v.y * M0[j].y;
-                d0.y += v.x * M0[j].y - v.y * M0[j].x;
-                d1.x += v.x * M1[j].x + v.y * M1[j].y;
-                d1.y += v.x * M1[j].y - v.y * M1[j].x;
+                d0.x = fmaf(v.x, M0[j].x, d0.x); d0.x = fmaf(v.y, M0[j].y, d0.x);
+                d0.y = fmaf(v.x, M0[j].y, d0.y); d0.y = fmaf(-v.y, M0[j].x, d0.y);
+                d1.x = fmaf(v.x, M1[j].x, d1.x); d1.x = fmaf(v.y, M1[j].y, d1.x);
+                d1.y = fmaf(v.x, M1[j].y, d1.y); d1.y = fmaf(-v.y, M1[j].x, d1.y);
             }
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) {
@@ -730,10 +714,10 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
 #pragma unroll
             for (int j = jm; j < NR; ++j) {
                 const float2 v = vv[j];
-                M0[j].x -= t0.x * v.x - t0.y * v.y;
-                M0[j].y -= t0.x * v.y + t0.y * v.x;
-                M1[j].x -= t1.x * v.x - t1.y * v.y;
-                M1[j].y -= t1.x * v.y + t1.y * v.x;
+                M0[j].x = fmaf(-t0.x, v.x, M0[j].x); M0[j].x = fmaf(t0.y, v.y, M0[j].x);
+                M0[j].y = fmaf(-t0.x, v.y, M0[j].y); M0[j].y = fmaf(-t0.y, v.x, M0[j].y);
+                M1[j].x = fmaf(-t1.x, v.x, M1[j].x); M1[j].x = fmaf(t1.y, v.y, M1[j].x);
+                M1[j].y = fmaf(-t1.x, v.y, M1[j].y); M1[j].y = fmaf(-t1.y, v.x, M1[j].y);
             }
         }
     }
@@ -783,8 +767,10 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int yv = 0; yv < 4; ++yv) {
-                    acc[x][yv].x += av[x].x * bv[yv].x + av[x].y * bv[yv].y;
-                    acc[x][yv].y += av[x].y * bv[yv].x - av[x].x * bv[yv].y;
+                    acc[x][yv].x = fmaf(av[x].x, bv[yv].x, acc[x][yv].x);
+                    acc[x][yv].x = fmaf(av[x].y, bv[yv].y, acc[x][yv].x);
+                    acc[x][yv].y = fmaf(av[x].y, bv[yv].x, acc[x][yv].y);
+                    acc[x][yv].y = fmaf(-av[x].x, bv[yv].y, acc[x][yv].y);
                 }
         }
 #pragma unroll
