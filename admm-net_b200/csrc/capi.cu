@@ -373,13 +373,19 @@ extern "C" int peak_search_full(const void* phi, int phi_is_c128, int B, int xba
     if (xbase < 1 || ybase < 1 || xbase > PEAK_MAX_BASE || ybase > PEAK_MAX_BASE)
         return fail(ADMMNET_ERR_ARG, "xbase/ybase must be in [1,32]");
     if (topl > 0 && !top) return fail(ADMMNET_ERR_ARG, "top is NULL");
-    const size_t sm = peak_smem_bytes(Gx, Gy, xbase, ybase, pmax);
-    if (sm > 227 * 1024) return fail(ADMMNET_ERR_ARG, "coarse grid too large for one CTA's shared memory");
+    const size_t sm0 = peak_smem_bytes(Gx, Gy, xbase, ybase, pmax);
+    const size_t per_peak = peak_refine_bytes_per_peak(xbase, ybase);
+    if (sm0 + 4 * per_peak > 227 * 1024) return fail(ADMMNET_ERR_ARG, "coarse grid too large for one CTA's shared memory");
+    int ptile = (int)((227 * 1024 - sm0) / per_peak);
+    if (ptile > 64) ptile = 64;
+    if ((size_t)ptile * per_peak > 72 * 1024) ptile = (int)(72 * 1024 / per_peak);
+    if (ptile < 4) ptile = 4;
+    const size_t sm = sm0 + (size_t)ptile * per_peak + 16;
     PeakArgs a;
     a.phi = phi; a.phi_is_c128 = phi_is_c128; a.B = B; a.xb = xbase; a.yb = ybase;
     a.axis_x = axis_x; a.axis_y = axis_y; a.Gx = Gx; a.Gy = Gy;
     a.xmin = xmin; a.xmax = xmax; a.xstep = xstep; a.ymin = ymin; a.ymax = ymax; a.ystep = ystep;
-    a.reducefactor = reducefactor; a.iters = iters; a.pmax = pmax; a.peaks = peaks; a.count = count;
+    a.reducefactor = reducefactor; a.iters = iters; a.pmax = pmax; a.ptile = ptile; a.peaks = peaks; a.count = count;
     a.topl = topl; a.top = top; a.surface = surface; a.status = status_dev;
     CK(cudaFuncSetAttribute(k_peak_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     prof::Scope pscope(prof::PEAK, (cudaStream_t)stream);

@@ -23,6 +23,7 @@ struct PeakArgs {
     double xmin, xmax, xstep, ymin, ymax, ystep, reducefactor;
     int iters;
     int pmax;              // capacity of peaks per signal
+    int ptile;             // peaks refined per block-wide round (sizes the refinement scratch)
     double* peaks;         // [B][pmax][3]  (x, y, height), discovery order
     int* count;            // [B]
     int topl;              // 0 = skip
@@ -95,8 +96,12 @@ __host__ __device__ inline size_t peak_smem_bytes(int Gx, int Gy, int xb, int yb
     size_t dbl = (((size_t)Gx * Gy + 1) & ~(size_t)1)   // Z (padded: the double2 arrays behind it need 16 B alignment)
                  + 2 * ((size_t)Gy * yb + (size_t)Gx * xb + (size_t)Gy * xb + (size_t)xb * yb)   // Sy, Dx, T, phi
                  + 64;                      // reductions
-    size_t bytes = dbl * 8 + (size_t)Gx * Gy /*flags*/ + 16 + (256 + 8) * 4 /*scan*/ + (size_t)pmax * 4;
+    size_t bytes = dbl * 8 + (((size_t)Gx * Gy + 15) & ~(size_t)15) /*flags*/ + 16 + (256 + 8) * 4 /*scan*/ +
+                   (((size_t)pmax * 4 + 15) & ~(size_t)15);
     return (bytes + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t peak_refine_bytes_per_peak(int xb, int yb) {
+    return 16 /*x0,y0*/ + 128 /*vals*/ + (size_t)4 * yb * 16 + (size_t)8 * xb * 16 + 8 /*nx,ny*/;
 }
 
 __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     double* redd = reinterpret_cast<double*>(phis + n);        // [64]
     int* scan = reinterpret_cast<int*>(redd + 64);             // [256+8]
     int* plist = scan + 256 + 8;                               // [pmax] flat pixel index of each peak
-    unsigned char* flag = reinterpret_cast<unsigned char*>(plist + a.pmax);   // [N]
+    unsigned char* flag = reinterpret_cast<unsigned char*>(plist + ((a.pmax + 3) & ~3));   // [N], 16 B aligned
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int sig = blockIdx.x;
 
@@ -221,40 +226,125 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     }
     __syncthreads();
 
-    // ---- refinement: one warp per peak, lanes over the local grid points
+    // ---- refinement (peakSearchUtils.py:136-171), tiles of PT peaks, block-wide phases per round:
+    //   R1 window per peak -> R2 steering vectors of the <=4+4 distinct local y/x values -> R3 row sums
+    //   t_q(y) -> R4 the <=16 local values -> R5 first-occurrence argmax.  Windows wider than 4 points per
+    //   axis (cannot happen for reducefactor <= 1/2, kept for generality) take the scalar fallback.
     double* out = a.peaks + (size_t)sig * a.pmax * 3;
-    for (int k = wid; k < Pst; k += 8) {
+    const int PT = a.ptile;
+    double* rx0 = reinterpret_cast<double*>(flag + ((N + 15) & ~15));      // [PT]
+    double* ry0 = rx0 + PT;                                                // [PT]
+    double* vals = ry0 + PT;                                               // [PT][16]
+    double2* svec = reinterpret_cast<double2*>(vals + 16 * PT);            // [PT][4][yb]
+    double2* dvec = svec + (size_t)PT * 4 * yb;                            // [PT][4][xb]
+    double2* tvec = dvec + (size_t)PT * 4 * xb;                            // [PT][4][xb]
+    int* rnx = reinterpret_cast<int*>(tvec + (size_t)PT * 4 * xb);         // [PT]
+    int* rny = rnx + PT;                                                   // [PT]
+    for (int k = tid; k < Pst; k += 256) {
         const int pix = plist[k];
-        double px = a.axis_x[pix % Gx], py = a.axis_y[pix / Gx], ph = 0.0;
+        out[3 * k] = a.axis_x[pix % Gx];
+        out[3 * k + 1] = a.axis_y[pix / Gx];
+        out[3 * k + 2] = 0.0;
+    }
+    __syncthreads();
+    for (int base = 0; base < Pst; base += PT) {
+        const int np = min(PT, Pst - base);
         double lx = a.xstep, ly = a.ystep;
         for (int it = 0; it < a.iters; ++it) {
             lx = __dmul_rn(a.reducefactor, lx);
             ly = __dmul_rn(a.reducefactor, ly);
-            const double x0 = fmax(a.xmin, __dsub_rn(px, lx)), x1 = fmin(__dsub_rn(a.xmax, lx), __dadd_rn(px, lx));
-            const double y0 = fmax(a.ymin, __dsub_rn(py, ly)), y1 = fmin(__dsub_rn(a.ymax, ly), __dadd_rn(py, ly));
-            if (x0 >= x1 || y0 >= y1) continue;
-            const int nx = np_arange_len(x0, x1, lx), ny = np_arange_len(y0, y1, ly);
-            if (nx == 0 || ny == 0) continue;
-            double best = -INFINITY;
-            int bidx = 0x7fffffff;
-            for (int q = lane; q < nx * ny; q += 32) {
-                const double xv = np_arange_val(x0, lx, q % nx), yv = np_arange_val(y0, ly, q / nx);
-                const double z = spectrum_point(phis, xb, yb, xv, yv);
-                if (z > best) { best = z; bidx = q; }      // q increases: first occurrence kept
+            // R1
+            for (int j = tid; j < np; j += 256) {
+                const int k = base + j;
+                const double px = out[3 * k], py = out[3 * k + 1];
+                const double x0 = fmax(a.xmin, __dsub_rn(px, lx)), x1 = fmin(__dsub_rn(a.xmax, lx), __dadd_rn(px, lx));
+                const double y0 = fmax(a.ymin, __dsub_rn(py, ly)), y1 = fmin(__dsub_rn(a.ymax, ly), __dadd_rn(py, ly));
+                int nx = 0, ny = 0;
+                if (!(x0 >= x1 || y0 >= y1)) {
+                    nx = np_arange_len(x0, x1, lx);
+                    ny = np_arange_len(y0, y1, ly);
+                    if (nx == 0 || ny == 0) nx = ny = 0;
+                }
+                if (nx > 4 || ny > 4) {                      // scalar fallback, any window size
+                    double best = -INFINITY;
+                    int bidx = -1;
+                    for (int q = 0; q < nx * ny; ++q) {
+                        const double z = spectrum_point(phis, xb, yb, np_arange_val(x0, lx, q % nx), np_arange_val(y0, ly, q / nx));
+                        if (z > best) { best = z; bidx = q; }
+                    }
+                    if (bidx >= 0) {
+                        out[3 * k] = np_arange_val(x0, lx, bidx % nx);
+                        out[3 * k + 1] = np_arange_val(y0, ly, bidx / nx);
+                        out[3 * k + 2] = best;
+                    }
+                    nx = ny = 0;
+                }
+                rx0[j] = x0; ry0[j] = y0; rnx[j] = nx; rny[j] = ny;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+            __syncthreads();
+            // R2: steering vectors
+            for (int i = tid; i < np * 4 * (yb + xb); i += 256) {
+                const int j = i / (4 * (yb + xb)), rem = i % (4 * (yb + xb));
+                if (rem < 4 * yb) {
+                    const int iy = rem / yb, pp = rem % yb;
+                    if (iy < rny[j]) svec[((size_t)j * 4 + iy) * yb + pp] = steer(np_arange_val(ry0[j], ly, iy), pp, yb);
+                } else {
+                    const int r2 = rem - 4 * yb, ix = r2 / xb, qq = r2 % xb;
+                    if (ix < rnx[j]) dvec[((size_t)j * 4 + ix) * xb + qq] = steer(np_arange_val(rx0[j], lx, ix), qq, xb);
+                }
             }
-            if (bidx != 0x7fffffff) {
-                px = np_arange_val(x0, lx, bidx % nx);
-                py = np_arange_val(y0, ly, bidx / nx);
-                ph = best;
+            __syncthreads();
+            // R3: t[iy][q] = sum_p conj(phi[p][q]) s_p(y_iy)
+            for (int i = tid; i < np * 4 * xb; i += 256) {
+                const int j = i / (4 * xb), iy = (i / xb) & 3, qq = i % xb;
+                if (iy < rny[j]) {
+                    const double2* sv = svec + ((size_t)j * 4 + iy) * yb;
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int pp = 0; pp < yb; ++pp) {
+                        const double2 ph = phis[pp * xb + qq], sp = sv[pp];
+                        acc.x += ph.x * sp.x + ph.y * sp.y;
+                        acc.y += ph.x * sp.y - ph.y * sp.x;
+                    }
+                    tvec[((size_t)j * 4 + iy) * xb + qq] = acc;
+                }
             }
+            __syncthreads();
+            // R4: local surface values
+            for (int i = tid; i < np * 16; i += 256) {
+                const int j = i >> 4, iy = (i >> 2) & 3, ix = i & 3;
+                if (iy < rny[j] && ix < rnx[j]) {
+                    const double2* tv = tvec + ((size_t)j * 4 + iy) * xb;
+                    const double2* dv = dvec + ((size_t)j * 4 + ix) * xb;
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int qq = 0; qq < xb; ++qq) {
+                        acc.x += tv[qq].x * dv[qq].x + tv[qq].y * dv[qq].y;
+                        acc.y += tv[qq].y * dv[qq].x - tv[qq].x * dv[qq].y;
+                    }
+                    vals[i] = abs2_np(acc);
+                }
+            }
+            __syncthreads();
+            // R5: first-occurrence maximum in row-major order
+            for (int j = tid; j < np; j += 256) {
+                const int nx = rnx[j], ny = rny[j];
+                if (nx > 0) {
+                    double best = -INFINITY;
+                    int bx = -1, by = -1;
+                    for (int iy = 0; iy < ny; ++iy)
+                        for (int ix = 0; ix < nx; ++ix) {
+                            const double z = vals[j * 16 + iy * 4 + ix];
+                            if (z > best) { best = z; bx = ix; by = iy; }
+                        }
+                    if (bx >= 0) {
+                        const int k = base + j;
+                        out[3 * k] = np_arange_val(rx0[j], lx, bx);
+                        out[3 * k + 1] = np_arange_val(ry0[j], ly, by);
+                        out[3 * k + 2] = best;
+                    }
+                }
+            }
+            __syncthreads();
         }
-        if (lane == 0) { out[3 * k] = px; out[3 * k + 1] = py; out[3 * k + 2] = ph; }
     }
     if (a.topl <= 0) return;
     __syncthreads();
