@@ -18,6 +18,7 @@ _PROTOS = {
     "admmnet_ws_scalars": (_i, [_vp, _sz, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "admmnet_set_mean": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _d, _vp]),
     "admmnet_final_phi": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "admmnet_reset_status": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "admmnet_status": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _vp, C.POINTER(_i)]),
     "admmnet_eigh_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "admmnet_eigh_batched": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp, _vp]),

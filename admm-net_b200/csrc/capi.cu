@@ -1,5 +1,6 @@
 // extern "C" boundary (include/admmnet_b200.h): argument checks, workspace carving, launches.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -99,6 +100,7 @@ struct Ws {
     size_t bytes;
 };
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+constexpr int NSLOT = 2;
 inline int default_rcap(int d) { return ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
 
 // n = signal length (for phi/h), d = matrix order.  Per-signal STATE arrays (Zp, GV, phi_cur, h_cur, r) cover
@@ -111,16 +113,17 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     auto take = [&](size_t nbytes) { unsigned char* q = p + off; off += al(nbytes); return q; };
     w.Zp = (float2*)take(B * npk * sizeof(float2));
     w.GV = (float2*)take(B * npk * sizeof(float2));
-    w.Zr = (float*)take((size_t)C * d * d * sizeof(float));
-    w.rot = (float2*)take((size_t)C * rcap * sizeof(float2));
-    w.tau = (float2*)take((size_t)C * d * sizeof(float2));
-    w.lam = (float*)take((size_t)C * d * sizeof(float));
-    w.dT = (float*)take((size_t)C * d * sizeof(float));
-    w.eT = (float*)take((size_t)C * d * sizeof(float));
+    // two scratch slots so that consecutive chunks can be in flight on different streams
+    w.Zr = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
+    w.rot = (float2*)take((size_t)NSLOT * C * rcap * sizeof(float2));
+    w.tau = (float2*)take((size_t)NSLOT * C * d * sizeof(float2));
+    w.lam = (float*)take((size_t)NSLOT * C * d * sizeof(float));
+    w.dT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
+    w.eT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
     w.phi_cur = (float2*)take((size_t)B * n * sizeof(float2));
     w.h_cur = (float*)take((size_t)B * n * sizeof(float));
     w.r = (float*)take((size_t)B * sizeof(float));
-    w.nrot = (int*)take((size_t)C * sizeof(int));
+    w.nrot = (int*)take((size_t)NSLOT * C * sizeof(int));
     w.rsum = (double*)take((size_t)(K + 1) * sizeof(double));
     w.mean = (float*)take((size_t)(K + 1) * sizeof(float));
     w.status = (int*)take(sizeof(int));
@@ -139,14 +142,26 @@ int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
 
 // the three eigen-solver launches after the tridiagonal form is in the workspace
 int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk, int with_c, float2* U_out,
-                    float* lamp_out, int* status, cudaStream_t st) {
+                    float* lamp_out, int* status, cudaStream_t st, cudaStream_t qst = nullptr,
+                    cudaEvent_t ev_in = nullptr, cudaEvent_t ev_out = nullptr) {
+    const bool side = qst != nullptr;
+    if (side) {   // k_ql on a high-priority side stream: it is latency bound and co-resides with other kernels
+        CK(cudaEventRecord(ev_in, st));
+        CK(cudaStreamWaitEvent(qst, ev_in, 0));
+    }
     {
+        cudaStream_t st_main = st;
+        cudaStream_t st = side ? qst : st_main;
         const size_t sm = (size_t)2 * d * QL_THREADS * sizeof(double);
         CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
                                                                          status);
         CK(cudaGetLastError());
+    }
+    if (side) {
+        CK(cudaEventRecord(ev_out, qst));
+        CK(cudaStreamWaitEvent(st, ev_out, 0));
     }
     {
         const size_t sm = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (4 * ((d + 3) / 4)) * sizeof(float);
@@ -176,9 +191,16 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
 }  // namespace
 
 // view of the workspace for the chunk [off, off+Bc): state pointers advanced, scratch untouched
-static Ws chunk_view(const Ws& w, int off, int n, int d) {
+static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0, int rcap = 0) {
     Ws c = w;
     const size_t npk = (size_t)d * (d + 1) / 2;
+    c.Zr += (size_t)slot * C * d * d;
+    c.rot += (size_t)slot * C * rcap;
+    c.tau += (size_t)slot * C * d;
+    c.lam += (size_t)slot * C * d;
+    c.dT += (size_t)slot * C * d;
+    c.eT += (size_t)slot * C * d;
+    c.nrot += (size_t)slot * C;
     c.Zp += (size_t)off * npk;
     c.GV += (size_t)off * npk;
     c.phi_cur += (size_t)off * n;
@@ -205,9 +227,54 @@ extern "C" int admmnet_ws_scalars(void* ws, size_t ws_bytes, int B, int chunk, i
     return 0;
 }
 
+// Internal streams for admmnet_forward: two chunk lanes (consecutive chunks of a layer overlap) and one
+// high-priority side stream per lane for the latency-bound k_ql.  Created lazily, one set per device.
+namespace {
+struct Lanes {
+    bool init = false;
+    cudaStream_t L[NSLOT], Q[NSLOT];
+    cudaEvent_t evH[NSLOT], evQ[NSLOT], evDone[NSLOT], evStart, evMean, evEnd;
+};
+Lanes g_lanes[16];
+int get_lanes(Lanes** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return fail(ADMMNET_ERR_ARG, "device ordinal out of range");
+    Lanes& l = g_lanes[dev];
+    if (!l.init) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < NSLOT; ++i) {
+            CK(cudaStreamCreateWithPriority(&l.L[i], cudaStreamNonBlocking, lo));
+            CK(cudaStreamCreateWithPriority(&l.Q[i], cudaStreamNonBlocking, hi));
+            CK(cudaEventCreateWithFlags(&l.evH[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&l.evQ[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&l.evDone[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&l.evStart, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l.evMean, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l.evEnd, cudaEventDisableTiming));
+        l.init = true;
+    }
+    *out = &l;
+    return 0;
+}
+}  // namespace
+
+static int layer_chunk_impl(const void* y, const void* b, const float* sigma, int B, int chunk, int sig_off, int Bc,
+                            int Mdim, int Ndim, int K, int k, const float* params, void* ws, size_t ws_bytes, int rcap,
+                            cudaStream_t st, int slot, cudaStream_t qst, cudaEvent_t ev_in, cudaEvent_t ev_out);
+
 extern "C" int admmnet_layer_chunk(const void* y, const void* b, const float* sigma, int B, int chunk, int sig_off,
                                    int Bc, int Mdim, int Ndim, int K, int k, const float* params, void* ws,
                                    size_t ws_bytes, int rcap, void* stream) {
+    return layer_chunk_impl(y, b, sigma, B, chunk, sig_off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
+                            (cudaStream_t)stream, 0, nullptr, nullptr, nullptr);
+}
+
+static int layer_chunk_impl(const void* y, const void* b, const float* sigma, int B, int chunk, int sig_off, int Bc,
+                            int Mdim, int Ndim, int K, int k, const float* params, void* ws, size_t ws_bytes, int rcap,
+                            cudaStream_t st, int slot, cudaStream_t qst, cudaEvent_t ev_in, cudaEvent_t ev_out) {
     const int n = Mdim * Ndim, d = n + 1;
     if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
     if (!y || !b || !sigma || !params) return fail(ADMMNET_ERR_ARG, "null input pointer");
@@ -215,10 +282,8 @@ extern "C" int admmnet_layer_chunk(const void* y, const void* b, const float* si
     if (sig_off < 0 || Bc <= 0 || Bc > chunk || sig_off + Bc > B) return fail(ADMMNET_ERR_ARG, "bad chunk range");
     Ws wf = carve(ws, B, chunk, n, d, K, rcap);
     if (!ws || ws_bytes < wf.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
-    Ws w = chunk_view(wf, sig_off, n, d);
-    cudaStream_t st = (cudaStream_t)stream;
+    Ws w = chunk_view(wf, sig_off, n, d, slot, chunk, rcap);
     const int ps = param_stride(n);
-    if (k == 0 && sig_off == 0) CK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
     HeadArgs h;
     h.y = (const float2*)y + (size_t)sig_off * n; h.b = (const float2*)b + (size_t)sig_off * n; h.sigma = sigma + sig_off;
     h.Zp = w.Zp; h.GV = w.GV; h.phi_cur = w.phi_cur; h.h_cur = w.h_cur; h.r_prev = w.r;
@@ -233,7 +298,15 @@ extern "C" int admmnet_layer_chunk(const void* y, const void* b, const float* si
         k_head<<<Bc, 256, sm, st>>>(h);
     }
     CK(cudaGetLastError());
-    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st);
+    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out);
+}
+
+extern "C" int admmnet_reset_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream) {
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    Ws w = carve(ws, B, chunk, n, n + 1, K, rcap);
+    if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
+    CK(cudaMemsetAsync(w.status, 0, sizeof(int), (cudaStream_t)stream));
+    return 0;
 }
 
 extern "C" int admmnet_layer_rsum(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k,
@@ -274,7 +347,6 @@ extern "C" int admmnet_final_phi(const void* y, const void* b, int B, int chunk,
     f.Pk = params + (size_t)(K - 1) * ps; f.Pkm1 = K > 1 ? params + (size_t)(K - 2) * ps : params;
     f.phi_out = (float2*)phi_out; f.B = B; f.n = n; f.d = d; f.first = (K == 1);
     cudaStream_t st = (cudaStream_t)stream;
-    if (K == 1) CK(cudaMemsetAsync(w.status, 0, sizeof(int), st));
     const long long nthreads = (long long)B * 32;
     prof::Scope pscope(prof::MISC, st);
     k_final_phi<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(f);
@@ -287,17 +359,50 @@ extern "C" int admmnet_forward(const void* y, const void* b, const float* sigma,
                                void* stream) {
     const int n = Mdim * Ndim;
     if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (int e = admmnet_reset_status(ws, ws_bytes, B, chunk, n, K, rcap, stream)) return e;
+    static const bool use_lanes = !(getenv("ADMMNET_LANES") && atoi(getenv("ADMMNET_LANES")) == 0);
+    if (!use_lanes) {      // single-stream variant (profiling): every launch on the caller's stream
+        for (int k = 0; k < K - 1; ++k) {
+            for (int off = 0; off < B; off += chunk) {
+                const int Bc = B - off < chunk ? B - off : chunk;
+                if (int e = admmnet_layer_chunk(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes,
+                                                rcap, stream))
+                    return e;
+            }
+            if (int e = admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, stream)) return e;
+            if (int e = admmnet_set_mean(ws, ws_bytes, B, chunk, n, K, rcap, k, (double)B, stream)) return e;
+        }
+        return admmnet_final_phi(y, b, B, chunk, Mdim, Ndim, K, params, phi_out, ws, ws_bytes, rcap, stream);
+    }
+    Lanes* ln = nullptr;
+    if (int e = get_lanes(&ln)) return e;
+    // fork: the lanes start after everything already queued on the caller's stream
+    CK(cudaEventRecord(ln->evStart, cs));
+    for (int i = 0; i < NSLOT; ++i) CK(cudaStreamWaitEvent(ln->L[i], ln->evStart, 0));
     for (int k = 0; k < K - 1; ++k) {
-        for (int off = 0; off < B; off += chunk) {
+        int c = 0;
+        for (int off = 0; off < B; off += chunk, ++c) {
             const int Bc = B - off < chunk ? B - off : chunk;
-            if (int e = admmnet_layer_chunk(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
-                                            stream))
+            const int s = c % NSLOT;
+            if (int e = layer_chunk_impl(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
+                                         ln->L[s], s, ln->Q[s], ln->evH[s], ln->evQ[s]))
                 return e;
         }
-        if (int e = admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, stream)) return e;
-        if (int e = admmnet_set_mean(ws, ws_bytes, B, chunk, n, K, rcap, k, (double)B, stream)) return e;
+        // join the lanes on lane 0, reduce the residual norms there, release the other lanes
+        for (int i = 1; i < NSLOT; ++i) {
+            CK(cudaEventRecord(ln->evDone[i], ln->L[i]));
+            CK(cudaStreamWaitEvent(ln->L[0], ln->evDone[i], 0));
+        }
+        if (int e = admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, ln->L[0])) return e;
+        if (int e = admmnet_set_mean(ws, ws_bytes, B, chunk, n, K, rcap, k, (double)B, ln->L[0])) return e;
+        CK(cudaEventRecord(ln->evMean, ln->L[0]));
+        for (int i = 1; i < NSLOT; ++i) CK(cudaStreamWaitEvent(ln->L[i], ln->evMean, 0));
     }
-    return admmnet_final_phi(y, b, B, chunk, Mdim, Ndim, K, params, phi_out, ws, ws_bytes, rcap, stream);
+    if (int e = admmnet_final_phi(y, b, B, chunk, Mdim, Ndim, K, params, phi_out, ws, ws_bytes, rcap, ln->L[0])) return e;
+    CK(cudaEventRecord(ln->evEnd, ln->L[0]));
+    CK(cudaStreamWaitEvent(cs, ln->evEnd, 0));
+    return 0;
 }
 
 extern "C" int admmnet_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream,
@@ -389,7 +494,7 @@ extern "C" int peak_search_full(const void* phi, int phi_is_c128, int B, int xba
     a.topl = topl; a.top = top; a.surface = surface; a.status = status_dev;
     CK(cudaFuncSetAttribute(k_peak_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     prof::Scope pscope(prof::PEAK, (cudaStream_t)stream);
-    k_peak_search<<<B, 256, sm, (cudaStream_t)stream>>>(a);
+    k_peak_search<<<B, PEAK_NT, sm, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return 0;
 }

@@ -404,9 +404,15 @@ k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, flo
 // Stream format per signal (float2 entries): [header (m, cnt as int bits)] [cnt x (c,s)] ... [header m=-1].
 // A sweep starting at m applies rotations to column pairs (i,i+1), i = m-1, m-2, ..., m-cnt.
 // =====================================================================================
-#define QL_THREADS 64
+#define QL_THREADS 32
 #define QL_MAXIT 60
 
+// Written as a per-lane state machine (one plane rotation per trip of a common loop) so that the 32
+// signals of a warp, whose sweeps have different lengths, all make progress on every trip instead of
+// waiting at the reconvergence point of divergent inner loops.  The deflation test is fused into the
+// sweep (every off-diagonal of the active block is rewritten by the sweep, so the smallest negligible
+// index is known when the sweep ends); a scan is only needed at the start and in the rare case of
+// three simultaneous deflations.
 __global__ void __launch_bounds__(QL_THREADS)
 k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, float* __restrict__ lam,
      float2* __restrict__ rot, int rcap, int* __restrict__ nrot, int* __restrict__ status) {
@@ -415,49 +421,84 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
     double* se = sd + (size_t)d * QL_THREADS;
     const int t = threadIdx.x;
     const int sig = blockIdx.x * QL_THREADS + t;
-    if (sig >= B) return;
+    const bool valid = sig < B;
 #define D_(i) sd[(i) * QL_THREADS + t]
 #define E_(i) se[(i) * QL_THREADS + t]
     double anorm = 0.0;
     for (int i = 0; i < d; ++i) {
-        const double di = dT[(size_t)i * B + sig], ei = eT[(size_t)i * B + sig];
+        const double di = valid ? dT[(size_t)i * B + sig] : 0.0, ei = valid ? eT[(size_t)i * B + sig] : 0.0;
         D_(i) = di;
         E_(i) = ei;
         anorm = fmax(anorm, fmax(fabs(di), fabs(ei)));
     }
     const double eps = 3.0e-8, floor_abs = 1.0e-9 * anorm;
-    float2* out = rot + (size_t)sig * rcap;
-    int nrec = 0;
+    float2* out = rot + (size_t)(valid ? sig : 0) * rcap;
+    enum { SEARCH = 0, START = 1, ROTATE = 2, DONE = 3 };
+    int phase = valid ? SEARCH : DONE;
+    int l = 0, m = 0, ms = 0, i = 0, iter = 0, hdr = 0, cnt = 0, nrec = 0;
+    int nm1 = 0, nm2 = 0;          // two smallest negligible indices seen in the current sweep
+    bool have2 = false;
+    double s = 1.0, c = 1.0, p = 0.0, g = 0.0;
     bool fail = false;
-    for (int l = 0; l < d && !fail; ++l) {
-        int iter = 0;
-        while (true) {
-            int m = l;
-            for (; m < d - 1; ++m) {
-                const double ddm = fabs(D_(m)) + fabs(D_(m + 1));
-                if (fabs(E_(m)) <= eps * ddm + floor_abs) break;
-            }
-            if (m == l) break;
-            if (iter++ == QL_MAXIT) { fail = true; break; }
-            double g = (D_(l + 1) - D_(l)) / (2.0 * E_(l));
-            double r = sqrt(g * g + 1.0);
-            g = D_(m) - D_(l) + E_(l) / (g + copysign(r, g));
-            double s = 1.0, c = 1.0, p = 0.0;
-            const int hdr = nrec++;
-            int cnt = 0;
-            bool early = false;
-            for (int i = m - 1; i >= l; --i) {
-                const double f = s * E_(i), bb = c * E_(i);
-                const double h2 = f * f + g * g;
-                if (h2 == 0.0) {
-                    E_(i + 1) = 0.0;
-                    D_(i + 1) -= p;
-                    E_(m) = 0.0;
-                    early = true;
-                    break;
+    while (!__all_sync(0xffffffffu, phase == DONE)) {
+        if (phase == SEARCH) {      // first negligible off-diagonal at or after ms (e[d-1] counts as 0)
+            bool found = false;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (!found) {
+                    if (ms >= d - 1) found = true;
+                    else if (fabs(E_(ms)) <= eps * (fabs(D_(ms)) + fabs(D_(ms + 1))) + floor_abs) found = true;
+                    else ++ms;
                 }
-                // 1/sqrt(h2): fp32 seed + two fp64 Newton steps (1e-7 -> 1e-14 -> 1e-28) instead of
-                // one sqrt and two divisions on the serial chain
+            }
+            if (found) { m = ms; have2 = false; phase = START; }
+        }
+        if (phase == START) {       // block [l, m]: converged eigenvalue or a new sweep
+            if (m == l) {
+                ++l;
+                iter = 0;
+                if (l >= d) phase = DONE;
+                else if (have2 && nm2 >= l) { m = nm2; have2 = false; }   // next block end known from the last sweep
+                else { ms = l; phase = SEARCH; }
+            } else if (iter++ == QL_MAXIT || nrec >= rcap - 2) {
+                fail = true;
+                phase = DONE;
+            } else {                // Wilkinson shift, sweep i = m-1 .. l
+                // g = d[m] - d[l] + e/(t + sign(t) sqrt(t^2+1)), t = delta/(2e)  ==  2e^2/(delta + sign(delta) hypot(delta, 2e))
+                const double el = E_(l), delta = D_(l + 1) - D_(l);
+                const double x = delta * delta + 4.0 * el * el;
+                double hyp;
+                if (x > 1e-30 && x < 1e30) {
+                    double ri = (double)rsqrtf((float)x);
+                    ri = ri * (1.5 - 0.5 * x * ri * ri);
+                    ri = ri * (1.5 - 0.5 * x * ri * ri);
+                    hyp = x * ri;
+                } else {
+                    hyp = sqrt(x);
+                }
+                const double den = delta + copysign(hyp, delta);
+                g = D_(m) - D_(l) + (2.0 * el * el) / den;
+                s = 1.0; c = 1.0; p = 0.0;
+                i = m - 1;
+                hdr = nrec++;
+                cnt = 0;
+                nm1 = m;
+                nm2 = m;
+                phase = ROTATE;
+            }
+        } else if (phase == ROTATE) {
+            const double ei = E_(i);
+            const double f = s * ei, bb = c * ei;
+            const double h2 = f * f + g * g;
+            bool end_sweep = false;
+            if (h2 == 0.0) {
+                E_(i + 1) = 0.0;
+                D_(i + 1) -= p;
+                E_(m) = 0.0;
+                nm2 = nm1; nm1 = i + 1;
+                end_sweep = true;
+            } else {
+                // 1/sqrt(h2): fp32 seed + two fp64 Newton steps instead of a sqrt and two divisions
                 double rinv;
                 if (h2 > 1e-30 && h2 < 1e30) {
                     rinv = (double)rsqrtf((float)h2);
@@ -466,35 +507,47 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
                 } else {
                     rinv = 1.0 / sqrt(h2);
                 }
-                r = h2 * rinv;
-                E_(i + 1) = r;
+                const double enew = h2 * rinv;
+                E_(i + 1) = enew;
                 s = f * rinv;
                 c = g * rinv;
-                g = D_(i + 1) - p;
-                r = (D_(i) - g) * s + 2.0 * c * bb;
+                const double di1 = D_(i + 1);
+                g = di1 - p;
+                const double r = (D_(i) - g) * s + 2.0 * c * bb;
                 p = s * r;
-                D_(i + 1) = g + p;
+                const double dnew = g + p;
+                D_(i + 1) = dnew;
                 g = c * r - bb;
+                // fused deflation test for e[i+1] (final for this sweep; e[m] itself is zeroed below)
+                if (i + 1 < m && enew <= eps * (fabs(dnew) + fabs(D_(i + 2))) + floor_abs) { nm2 = nm1; nm1 = i + 1; }
                 if (nrec < rcap - 1) out[nrec] = make_float2((float)c, (float)s);
                 ++nrec;
                 ++cnt;
+                --i;
+                if (i < l) {
+                    const double dl = D_(l) - p;
+                    D_(l) = dl;
+                    E_(l) = g;
+                    E_(m) = 0.0;
+                    if (fabs(g) <= eps * (fabs(dl) + fabs(D_(l + 1))) + floor_abs) { nm2 = nm1; nm1 = l; }
+                    end_sweep = true;
+                }
             }
-            if (!early) {
-                D_(l) -= p;
-                E_(l) = g;
-                E_(m) = 0.0;
+            if (end_sweep) {
+                if (hdr < rcap - 1) out[hdr] = make_float2(__int_as_float(m), __int_as_float(cnt));
+                if (nrec >= rcap - 1) { fail = true; phase = DONE; }
+                else { m = nm1; have2 = true; phase = START; }       // smallest negligible index in [l, old m]
             }
-            if (hdr < rcap - 1) out[hdr] = make_float2(__int_as_float(m), __int_as_float(cnt));
-            if (nrec >= rcap - 1) { fail = true; break; }
         }
     }
+    if (!valid) return;
     if (fail) {
         atomicOr(status, 1);
         nrec = 0;   // consumer leaves Z = I; the status word is the error report
     }
     out[nrec] = make_float2(__int_as_float(-1), __int_as_float(0));
     nrot[sig] = nrec + 1;
-    for (int i = 0; i < d; ++i) lam[(size_t)sig * d + i] = (float)D_(i);
+    for (int j = 0; j < d; ++j) lam[(size_t)sig * d + j] = (float)D_(j);
 #undef D_
 #undef E_
 }

@@ -104,7 +104,8 @@ __host__ __device__ inline size_t peak_refine_bytes_per_peak(int xb, int yb) {
     return 16 /*x0,y0*/ + 128 /*vals*/ + (size_t)4 * yb * 16 + (size_t)8 * xb * 16 + 8 /*nx,ny*/;
 }
 
-__global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
+#define PEAK_NT 512
+__global__ void __launch_bounds__(PEAK_NT) k_peak_search(PeakArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Gx = a.Gx, Gy = a.Gy, xb = a.xb, yb = a.yb, n = xb * yb, N = Gx * Gy;
     double* Z = reinterpret_cast<double*>(smem_raw);
@@ -119,18 +120,18 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int sig = blockIdx.x;
 
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += PEAK_NT) {
         if (a.phi_is_c128) phis[i] = reinterpret_cast<const double2*>(a.phi)[(size_t)sig * n + i];
         else {
             const float2 v = reinterpret_cast<const float2*>(a.phi)[(size_t)sig * n + i];
             phis[i] = make_double2((double)v.x, (double)v.y);
         }
     }
-    for (int i = tid; i < Gy * yb; i += 256) Sy[i] = steer(a.axis_y[i / yb], i % yb, yb);
-    for (int i = tid; i < Gx * xb; i += 256) Dx[i] = steer(a.axis_x[i / xb], i % xb, xb);
+    for (int i = tid; i < Gy * yb; i += PEAK_NT) Sy[i] = steer(a.axis_y[i / yb], i % yb, yb);
+    for (int i = tid; i < Gx * xb; i += PEAK_NT) Dx[i] = steer(a.axis_x[i % Gx], i / Gx, xb);   // [xb][Gx]
     __syncthreads();
     // T[iy][q] = sum_p conj(phi[p][q]) * Sy[iy][p]
-    for (int i = tid; i < Gy * xb; i += 256) {
+    for (int i = tid; i < Gy * xb; i += PEAK_NT) {
         const int iy = i / xb, q = i % xb;
         double2 acc = make_double2(0.0, 0.0);
         for (int p = 0; p < yb; ++p) {
@@ -142,11 +143,11 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     }
     __syncthreads();
     double lmin = INFINITY, lmax = -INFINITY;
-    for (int i = tid; i < N; i += 256) {
+    for (int i = tid; i < N; i += PEAK_NT) {
         const int iy = i / Gx, ix = i % Gx;
         double2 acc = make_double2(0.0, 0.0);
         for (int q = 0; q < xb; ++q) {
-            const double2 t = T[iy * xb + q], dq = Dx[ix * xb + q];
+            const double2 t = T[iy * xb + q], dq = Dx[q * Gx + ix];
             acc.x += t.x * dq.x + t.y * dq.y;
             acc.y += t.y * dq.x - t.x * dq.y;
         }
@@ -162,14 +163,14 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
         lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     }
-    if (lane == 0) { redd[wid] = lmin; redd[8 + wid] = lmax; }
+    if (lane == 0) { redd[wid] = lmin; redd[16 + wid] = lmax; }
     __syncthreads();
-    double gmin = redd[0], gmax = redd[8];
-    for (int w = 1; w < 8; ++w) { gmin = fmin(gmin, redd[w]); gmax = fmax(gmax, redd[8 + w]); }
+    double gmin = redd[0], gmax = redd[16];
+    for (int w = 1; w < PEAK_NT / 32; ++w) { gmin = fmin(gmin, redd[w]); gmax = fmax(gmax, redd[16 + w]); }
     const bool constant = !(gmax > gmin);
 
     // ---- candidates: no strictly greater 8-neighbour (outside the image counts as lower)
-    for (int i = tid; i < N; i += 256) {
+    for (int i = tid; i < N; i += PEAK_NT) {
         const int iy = i / Gx, ix = i % Gx;
         const double z = Z[i];
         bool cand = !constant;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     // ---- plateaus: a candidate with an equal-valued non-candidate neighbour is not a maximum
     for (int guard = 0; guard < N; ++guard) {
         int changed = 0;
-        for (int i = tid; i < N; i += 256) {
+        for (int i = tid; i < N; i += PEAK_NT) {
             if (!flag[i]) continue;
             const int iy = i / Gx, ix = i % Gx;
             const double z = Z[i];
@@ -202,10 +203,10 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     }
     // ---- ordered compaction (row-major == np.where order)
     const int seg = (N + 255) / 256;
-    const int s0 = min(N, tid * seg), s1 = min(N, s0 + seg);
+    const int s0 = tid < 256 ? min(N, tid * seg) : N, s1 = min(N, s0 + seg);
     int cnt = 0;
     for (int i = s0; i < s1; ++i) cnt += flag[i];
-    scan[tid] = cnt;
+    if (tid < 256) scan[tid] = cnt;
     __syncthreads();
     if (tid == 0) {
         int run = 0;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     __syncthreads();
     const int P = scan[256];
     const int Pst = min(P, a.pmax);
-    {
+    if (tid < 256) {
         int o = scan[tid];
         for (int i = s0; i < s1; ++i)
             if (flag[i]) { if (o < a.pmax) plist[o] = i; ++o; }
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     double2* tvec = dvec + (size_t)PT * 4 * xb;                            // [PT][4][xb]
     int* rnx = reinterpret_cast<int*>(tvec + (size_t)PT * 4 * xb);         // [PT]
     int* rny = rnx + PT;                                                   // [PT]
-    for (int k = tid; k < Pst; k += 256) {
+    for (int k = tid; k < Pst; k += PEAK_NT) {
         const int pix = plist[k];
         out[3 * k] = a.axis_x[pix % Gx];
         out[3 * k + 1] = a.axis_y[pix / Gx];
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
             lx = __dmul_rn(a.reducefactor, lx);
             ly = __dmul_rn(a.reducefactor, ly);
             // R1
-            for (int j = tid; j < np; j += 256) {
+            for (int j = tid; j < np; j += PEAK_NT) {
                 const int k = base + j;
                 const double px = out[3 * k], py = out[3 * k + 1];
                 const double x0 = fmax(a.xmin, __dsub_rn(px, lx)), x1 = fmin(__dsub_rn(a.xmax, lx), __dadd_rn(px, lx));
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
             }
             __syncthreads();
             // R2: steering vectors
-            for (int i = tid; i < np * 4 * (yb + xb); i += 256) {
+            for (int i = tid; i < np * 4 * (yb + xb); i += PEAK_NT) {
                 const int j = i / (4 * (yb + xb)), rem = i % (4 * (yb + xb));
                 if (rem < 4 * yb) {
                     const int iy = rem / yb, pp = rem % yb;
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
             }
             __syncthreads();
             // R3: t[iy][q] = sum_p conj(phi[p][q]) s_p(y_iy)
-            for (int i = tid; i < np * 4 * xb; i += 256) {
+            for (int i = tid; i < np * 4 * xb; i += PEAK_NT) {
                 const int j = i / (4 * xb), iy = (i / xb) & 3, qq = i % xb;
                 if (iy < rny[j]) {
                     const double2* sv = svec + ((size_t)j * 4 + iy) * yb;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
             }
             __syncthreads();
             // R4: local surface values
-            for (int i = tid; i < np * 16; i += 256) {
+            for (int i = tid; i < np * 16; i += PEAK_NT) {
                 const int j = i >> 4, iy = (i >> 2) & 3, ix = i & 3;
                 if (iy < rny[j] && ix < rnx[j]) {
                     const double2* tv = tvec + ((size_t)j * 4 + iy) * xb;
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
             }
             __syncthreads();
             // R5: first-occurrence maximum in row-major order
-            for (int j = tid; j < np; j += 256) {
+            for (int j = tid; j < np; j += PEAK_NT) {
                 const int nx = rnx[j], ny = rny[j];
                 if (nx > 0) {
                     double best = -INFINITY;
@@ -352,12 +353,12 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
     // ---- top-L by height (stable: ties keep discovery order)
     double* top = a.top + (size_t)sig * a.topl * 3;
     unsigned char* taken = flag;   // reuse
-    for (int i = tid; i < Pst; i += 256) taken[i] = 0;
+    for (int i = tid; i < Pst; i += PEAK_NT) taken[i] = 0;
     __syncthreads();
     for (int l = 0; l < a.topl; ++l) {
         double best = -INFINITY;
         int bi = 0x7fffffff;
-        for (int i = tid; i < Pst; i += 256)
+        for (int i = tid; i < Pst; i += PEAK_NT)
             if (!taken[i]) {
                 const double hgt = out[3 * i + 2];
                 if (hgt > best) { best = hgt; bi = i; }
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(256) k_peak_search(PeakArgs a) {
         __syncthreads();
         double gb = redd[0];
         int gi = scan[0];
-        for (int w = 1; w < 8; ++w) {
+        for (int w = 1; w < PEAK_NT / 32; ++w) {
             const double ob = redd[w];
             const int oi = scan[w];
             if (oi == 0x7fffffff) continue;

@@ -38,6 +38,8 @@ def run_layers(engine, num_layers, norm_scope="global", group=None):
         raise ValueError("norm_scope must be 'global' or 'shard'")
     use_dist = norm_scope == "global" and dist.is_available() and dist.is_initialized() and \
         dist.get_world_size(group) > 1
+    if hasattr(engine, "begin"):
+        engine.begin()
     total = float(engine.count())
     if use_dist:
         cnt = torch.tensor([total], dtype=torch.float64, device=engine.rsum(0).device)
@@ -67,6 +69,11 @@ class CudaEngine:
 
     def count(self):
         return self.B
+
+    def begin(self):
+        m, ws = self.m, self.ws
+        _capi.check(self.L.admmnet_reset_status(ws.ptr, ws.nbytes, self.B, self.chunk, m.M * m.N, m.num_layers, m.rcap,
+                                                self._stream()))
 
     def layer(self, k):
         m, ws = self.m, self.ws

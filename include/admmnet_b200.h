@@ -10,8 +10,11 @@
  *   - every function returns 0 on success, <0 on error; admmnet_last_error() (thread local) explains.
  *   - all data pointers are DEVICE pointers unless the name ends in _host; the caller owns every
  *     buffer; nothing is allocated behind the caller's back (query *_workspace_bytes first).
- *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); calls are re-entrant
- *     across streams given distinct workspaces.  No C++ exception crosses the ABI.
+ *   - work is ordered after everything queued on the caller's stream (cudaStream_t passed as void*)
+ *     and the stream waits for it; admmnet_forward additionally fans chunks out over library-owned
+ *     non-blocking streams (two chunk lanes + a high-priority lane for the latency-bound QL kernel)
+ *     between a fork and a join event.  Calls are re-entrant across streams given distinct
+ *     workspaces.  No C++ exception crosses the ABI.
  *   - complex64 = interleaved float pairs, complex128 = interleaved double pairs, row-major.
  */
 #ifndef ADMMNET_B200_H
@@ -72,6 +75,8 @@ int admmnet_set_mean(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, 
                      void* stream);
 int admmnet_final_phi(const void* y, const void* b, int B, int chunk, int Mdim, int Ndim, int K, const float* params,
                       void* phi_out, void* ws, size_t ws_bytes, int rcap, void* stream);
+/* clears the status word; call once before layer 0 when driving the split-phase API by hand */
+int admmnet_reset_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream);
 /* copies the status word to the host (synchronises the stream) */
 int admmnet_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream,
                    int* status_host);
