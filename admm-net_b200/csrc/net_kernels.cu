@@ -83,96 +83,124 @@ __device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, i
     }
 }
 
+// Per Householder step k (trailing block = rows/cols k+1..d-1, size m):
+//   warp 0 alone :  finish step k-1 (p = tau*sum(partials), w = p - (tau/2)(p^H v) v -> pending (v,w)),
+//                   then column k with the pending update applied -> d[k], reflector k (tau, v_new).
+//                   The rows it needs for the second half are the ones it just produced, so everything
+//                   stays in registers / warp shuffles: no block barrier inside this section.
+//   barrier
+//   all 8 warps  :  fused pass  A <- A - v w^H - w v^H  and  partial products  A v_new
+//   barrier
+// i.e. two block barriers per step.
 __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S, float2* tau_out, float* dd,
                              float* ee) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < 128) S.vw[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    for (int k = 0; k < d - 1; ++k) {
-        const int m = d - k - 1;            // trailing size, rows/cols k+1..d-1
-        float* red = S.red + (k & 1) * 32;
-        // ---- phase A: column k with the pending update applied; its norm
-        float2 a = make_float2(0.f, 0.f);
-        float ss = 0.f;
-        if (tid <= m) {
-            const int r = k + tid;
-            a = A[r + (size_t)k * ld];
-            const float4 tr = S.vw[r], tk = S.vw[k];
-            a.x -= tr.x * tk.z + tr.y * tk.w + tr.z * tk.x + tr.w * tk.y;
-            a.y -= tr.y * tk.z - tr.x * tk.w + tr.w * tk.x - tr.z * tk.y;
-            if (tid == 0) dd[k] = a.x;
-            if (tid == 1) S.scal[0] = a;
-            if (tid >= 2) ss = a.x * a.x + a.y * a.y;
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) red[wid] = ss;
-        __syncthreads();                                           // (1)
-        float tot = 0.f;
+    float2 tau_prev = make_float2(0.f, 0.f);
+    for (int k = 0; k < d; ++k) {
+        const int m = d - k - 1;            // trailing size of step k (m == 0: only the epilogue of step d-2)
+        if (wid == 0) {
+            // rows k..d-1 = local rows t = lane + 32 j of step k-1's trailing block
+            float2 vr[4], w[4];
+            const int mp = m + 1;
+            // ---- finish step k-1
+            if (k > 0) {
+                const int nq = mp > 32 ? 4 : 8;
+                float2 p[4];
+                float dx = 0.f, dy = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) tot += red[w];
-        const float2 alpha = S.scal[0];
-        float2 tau, scale;
-        float beta;
-        if (tot == 0.f && alpha.y == 0.f) {
-            tau = make_float2(0.f, 0.f);
-            scale = make_float2(0.f, 0.f);
-            beta = alpha.x;
-        } else {
-            beta = -copysignf(sqrtf(alpha.x * alpha.x + alpha.y * alpha.y + tot), alpha.x);
-            tau = make_float2((beta - alpha.x) / beta, -alpha.y / beta);
-            scale = cdiv(make_float2(1.f, 0.f), make_float2(alpha.x - beta, alpha.y));
-        }
-        if (tid >= 1 && tid <= m) {
-            const int r = k + tid;
-            float2 vi = make_float2(1.f, 0.f);
-            if (tid >= 2) {
-                vi = cmul(a, scale);
-                A[r + (size_t)k * ld] = vi;                        // kept for the export of the reflectors
+                for (int j = 0; j < 4; ++j) {
+                    const int t = lane + 32 * j;
+                    p[j] = make_float2(0.f, 0.f);
+                    vr[j] = make_float2(0.f, 0.f);
+                    if (t < mp) {
+                        float2 sacc = make_float2(0.f, 0.f);
+                        for (int qq = 0; qq < nq; ++qq) sacc = cadd(sacc, S.part[qq * 128 + t]);
+                        p[j] = cmul(tau_prev, sacc);
+                        vr[j] = S.vn[k + t];
+                        dx = fmaf(p[j].x, vr[j].x, dx); dx = fmaf(p[j].y, vr[j].y, dx);      // conj(p) * v
+                        dy = fmaf(p[j].x, vr[j].y, dy); dy = fmaf(-p[j].y, vr[j].x, dy);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dx += __shfl_xor_sync(0xffffffffu, dx, o);
+                    dy += __shfl_xor_sync(0xffffffffu, dy, o);
+                }
+                const float2 a2 = cmul(make_float2(-0.5f * tau_prev.x, -0.5f * tau_prev.y), make_float2(dx, dy));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = lane + 32 * j;
+                    w[j] = cadd(p[j], cmul(a2, vr[j]));
+                    if (t < mp) S.vw[k + t] = make_float4(vr[j].x, vr[j].y, w[j].x, w[j].y);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { vr[j] = make_float2(0.f, 0.f); w[j] = make_float2(0.f, 0.f); }
             }
-            S.vn[r] = vi;
+            // pending (v,w) of row k (local row 0: lane 0, slot 0)
+            const float vkx = __shfl_sync(0xffffffffu, vr[0].x, 0), vky = __shfl_sync(0xffffffffu, vr[0].y, 0);
+            const float wkx = __shfl_sync(0xffffffffu, w[0].x, 0), wky = __shfl_sync(0xffffffffu, w[0].y, 0);
+            // ---- column k with the pending update applied
+            float2 a[4];
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = lane + 32 * j;
+                a[j] = make_float2(0.f, 0.f);
+                if (t < mp) {
+                    float2 x = A[(k + t) + (size_t)k * ld];
+                    // x -= v_r conj(w_k) + w_r conj(v_k)
+                    x.x = fmaf(-vr[j].x, wkx, x.x); x.x = fmaf(-vr[j].y, wky, x.x);
+                    x.x = fmaf(-w[j].x, vkx, x.x);  x.x = fmaf(-w[j].y, vky, x.x);
+                    x.y = fmaf(-vr[j].y, wkx, x.y); x.y = fmaf(vr[j].x, wky, x.y);
+                    x.y = fmaf(-w[j].y, vkx, x.y);  x.y = fmaf(w[j].x, vky, x.y);
+                    a[j] = x;
+                    if (t >= 2) ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+                }
+            }
+            if (lane == 0) dd[k] = a[0].x;
+            if (m > 0) {
+                ss = warp_sum(ss);
+                const float2 alpha = make_float2(__shfl_sync(0xffffffffu, a[0].x, 1), __shfl_sync(0xffffffffu, a[0].y, 1));
+                float2 tau, scale;
+                float beta;
+                if (ss == 0.f && alpha.y == 0.f) {
+                    tau = make_float2(0.f, 0.f);
+                    scale = make_float2(0.f, 0.f);
+                    beta = alpha.x;
+                } else {
+                    beta = -copysignf(sqrtf(alpha.x * alpha.x + alpha.y * alpha.y + ss), alpha.x);
+                    tau = make_float2((beta - alpha.x) / beta, -alpha.y / beta);
+                    scale = cdiv(make_float2(1.f, 0.f), make_float2(alpha.x - beta, alpha.y));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = lane + 32 * j;
+                    if (t >= 1 && t < mp) {
+                        float2 vi = make_float2(1.f, 0.f);
+                        if (t >= 2) {
+                            vi = cmul(a[j], scale);
+                            A[(k + t) + (size_t)k * ld] = vi;          // kept for the export of the reflectors
+                        }
+                        S.vn[k + t] = vi;
+                    }
+                }
+                if (lane == 0) {
+                    tau_out[k] = tau;
+                    ee[k] = beta;
+                }
+                tau_prev = tau;
+            }
         }
-        if (tid == 0) {
-            tau_out[k] = tau;
-            ee[k] = beta;
-        }
-        __syncthreads();                                           // (2)
-        // ---- phase B: fused pending update + mat-vec with the new reflector
+        if (m == 0) break;
+        __syncthreads();
+        // ---- fused pending update + mat-vec with the new reflector
         if (m > 64) tri_fused_pass<2, 64>(A, ld, k, m, S);
         else if (m > 32) tri_fused_pass<1, 64>(A, ld, k, m, S);
         else tri_fused_pass<1, 32>(A, ld, k, m, S);
-        __syncthreads();                                           // (3)
-        // ---- phase C: p = tau * sum(partials); w = p - (tau/2)(p^H v) v
-        const int nq = m > 32 ? 4 : 8;
-        float2 p = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
-        float dx = 0.f, dy = 0.f;
-        if (tid < m) {
-            float2 sacc = make_float2(0.f, 0.f);
-            for (int qq = 0; qq < nq; ++qq) sacc = cadd(sacc, S.part[qq * 128 + tid]);
-            p = cmul(tau, sacc);
-            vr = S.vn[k + 1 + tid];
-            const float2 t = cconjmul(p, vr);
-            dx = t.x;
-            dy = t.y;
-        }
-        dx = warp_sum(dx);
-        dy = warp_sum(dy);
-        float* red2 = red + 8;
-        if (lane == 0) { red2[wid] = dx; red2[8 + wid] = dy; }
-        __syncthreads();                                           // (4)
-        float sx = 0.f, sy = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { sx += red2[w]; sy += red2[8 + w]; }
-        const float2 a2 = cmul(make_float2(-0.5f * tau.x, -0.5f * tau.y), make_float2(sx, sy));
-        if (tid < m) {
-            const float2 w = cadd(p, cmul(a2, vr));
-            S.vw[k + 1 + tid] = make_float4(vr.x, vr.y, w.x, w.y);
-        }
-        __syncthreads();                                           // (5)
-    }
-    if (tid == 0) {
-        const int r = d - 1;
-        const float4 t = S.vw[r];
-        dd[r] = A[r + (size_t)r * ld].x - 2.f * (t.x * t.z + t.y * t.w);
+        __syncthreads();
     }
     __syncthreads();
 }
