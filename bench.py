@@ -34,6 +34,9 @@ METRIC = "signals/s, ADMM-Net K=10 forward + peak search"
 FLOP_PER_LAYER = 33.1e6          # eigh 24 d^3 + rebuild 8 d^3 + 0.15 MFLOP elementwise
 FLOP_PEAK_SEARCH = 0.86e6        # separable coarse surface
 BYTES_PER_SIGNAL = 2404          # y 800 + b 800 + sigma 4 in, phi 800 out
+# implementation DRAM traffic of the four layer kernels per signal-layer, from the ncu --set full capture in
+# profiles/r01_ncu_summary.md (dram__bytes_read+write over 4096 signals): 157 + 53 + 98 + 114 KB
+TRAFFIC_PER_SIGNAL_LAYER = 421.8e3
 
 
 def tile_signals(B, seed):
@@ -296,7 +299,10 @@ def main():
         "roofline": {
             "bound": "fp32", "kernel": "layer pipeline k_head+k_ql+k_rot+k_tail (dominant: %s)" % dom,
             "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
-            "traffic": None,
+            "traffic": TRAFFIC_PER_SIGNAL_LAYER * (K_LAYERS - 1) * B,
+            "traffic_note": "bytes per step of the four layer kernels (profiles/r01_ncu_summary.md); algorithmic "
+                            "bytes per step are 2404 B x signals: the path is compute bound, the extra traffic is "
+                            "per-layer state (packed Z, G, reflectors, rotation stream) at <5 % of HBM bandwidth",
             "note": "FP32-FMA/shared-memory bound eigen-solver (SURVEY.md §8d): algorithmic 33.1 MFLOP per signal-layer x "
                     "(K-1) layers / summed CUDA-event time of the four kernels; peak = FP32 FFMA micro-kernel measured "
                     "live (MEASURED_PEAKS.json has no FP32 figure). launches per step: %d" % eig_launch,
