@@ -28,8 +28,8 @@ static int fail(int code, const std::string& msg) {
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
 // Process-global, not thread safe; off by default (then the only cost is one branch per launch).
 namespace prof {
-enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, NKINDS };
-static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search"};
+enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, NKINDS };
+static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2"};
 struct Rec { int kind; cudaEvent_t a, b; };
 static bool on = false;
 static std::vector<Rec> recs;
@@ -93,7 +93,7 @@ extern "C" int admmnet_param_stride(int n) { return param_stride(n); }
 // ------------------------------------------------------------------------------------ workspace
 namespace {
 struct Ws {
-    float2 *Zp, *GV, *rot, *tau, *phi_cur;
+    float2 *Zp, *GV, *rot, *tau, *phi_cur, *Ttr;
     float *Zr, *lam, *dT, *eT, *h_cur, *r, *mean;
     int *nrot, *status;
     double* rsum;
@@ -101,6 +101,8 @@ struct Ws {
 };
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int NSLOT = 2;
+constexpr int TR_MAX = 64;   // order of the trailing block handed to the second tridiagonalisation stage
+inline int stage1_steps(int d) { return d > TR_MAX + 8 ? d - TR_MAX : d - 1; }
 inline int default_rcap(int d) { return ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
 
 // n = signal length (for phi/h), d = matrix order.  Per-signal STATE arrays (Zp, GV, phi_cur, h_cur, r) cover
@@ -117,6 +119,7 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     w.Zr = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
     w.rot = (float2*)take((size_t)NSLOT * C * rcap * sizeof(float2));
     w.tau = (float2*)take((size_t)NSLOT * C * d * sizeof(float2));
+    w.Ttr = (float2*)take((size_t)NSLOT * C * TR_MAX * TR_MAX * sizeof(float2));
     w.lam = (float*)take((size_t)NSLOT * C * d * sizeof(float));
     w.dT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
     w.eT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
@@ -137,6 +140,21 @@ int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
     if (n < 2 || n > 127) return fail(ADMMNET_ERR_ARG, "n = M*N must be in [2,127] (matrix order d = n+1 <= 128)");
     if (rcap == 0) rcap = default_rcap(n + 1);
     if (rcap < 2048 || rcap % ROT_CHUNK) return fail(ADMMNET_ERR_ARG, "rcap must be a multiple of 1024, >= 2048");
+    return 0;
+}
+
+// second tridiagonalisation stage on the compacted trailing block (no-op when stage 1 did everything)
+int launch_head2(const Ws& w, int B, int d, cudaStream_t st) {
+    const int k1 = stage1_steps(d);
+    if (k1 >= d - 1) return 0;
+    Head2Args h;
+    h.Ttr = w.Ttr; h.GV = w.GV; h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
+    h.B = B; h.d = d; h.d2 = d - k1; h.ld2 = h.d2 | 1; h.k1 = k1;
+    const size_t sm = head2_smem_bytes(h.d2, h.ld2);
+    CK(cudaFuncSetAttribute(k_head2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    prof::Scope pscope(prof::HEAD2, st);
+    k_head2<<<B, 128, sm, st>>>(h);
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -197,6 +215,7 @@ static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0
     c.Zr += (size_t)slot * C * d * d;
     c.rot += (size_t)slot * C * rcap;
     c.tau += (size_t)slot * C * d;
+    c.Ttr += (size_t)slot * C * TR_MAX * TR_MAX;
     c.lam += (size_t)slot * C * d;
     c.dT += (size_t)slot * C * d;
     c.eT += (size_t)slot * C * d;
@@ -291,6 +310,7 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     h.Pk = params + (size_t)k * ps; h.Pkm1 = k > 0 ? params + (size_t)(k - 1) * ps : params;
     h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
     h.B = Bc; h.n = n; h.d = d; h.ld = d | 1; h.first = (k == 0);
+    h.Ttr = w.Ttr; h.k1 = stage1_steps(d);
     const size_t sm = head_smem_bytes(d, h.ld);
     CK(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     {
@@ -298,6 +318,7 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
         k_head<<<Bc, 256, sm, st>>>(h);
     }
     CK(cudaGetLastError());
+    if (int e = launch_head2(w, Bc, d, st)) return e;
     return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out);
 }
 
@@ -438,8 +459,9 @@ extern "C" int admmnet_eigh_batched(const void* A, int B, int d, float* evals, v
     const int ld = d | 1;
     const size_t sm = head_smem_bytes(d, ld);
     CK(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_tridiag<<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT);
+    k_tridiag<<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT, w.Ttr, stage1_steps(d));
     CK(cudaGetLastError());
+    if (int e = launch_head2(w, B, d, st)) return e;
     if (int e = launch_eig_tail(w, B, d - 1, d, rcap, params, params ? 0 : -1, (float2*)evecs, nullptr, status_dev, st))
         return e;
     const size_t npk = (size_t)d * (d + 1) / 2;

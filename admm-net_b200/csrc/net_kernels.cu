@@ -36,9 +36,9 @@ struct TriScratch {
 // One fused sweep over the trailing block (rows/cols k+1..d-1):
 //     A <- A - v w^H - w v^H   (pending update of the previous step)     and     part[q][r] = sum_c A[r][c] vn[c]
 // NROWS rows per thread (r, r+RSTRIDE); column groups q = tid / RSTRIDE, c = q, q+NQ, ...
-template <int NROWS, int RSTRIDE>
+template <int NROWS, int RSTRIDE, int NT, int PSTR>
 __device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, int k, int m, const TriScratch& S) {
-    constexpr int NQ = 256 / RSTRIDE;
+    constexpr int NQ = NT / RSTRIDE;
     const int tid = threadIdx.x;
     const int rr = tid & (RSTRIDE - 1), q = tid / RSTRIDE;
     const int g0 = k + 1;                       // global index of local row/col 0
@@ -79,7 +79,7 @@ __device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, i
 #pragma unroll
     for (int i = 0; i < NROWS; ++i) {
         const int rl = rr + i * RSTRIDE;
-        if (rl < 128) S.part[q * 128 + rl] = acc[i];
+        if (rl < PSTR) S.part[q * PSTR + rl] = acc[i];
     }
 }
 
@@ -92,21 +92,27 @@ __device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, i
 //   all 8 warps  :  fused pass  A <- A - v w^H - w v^H  and  partial products  A v_new
 //   barrier
 // i.e. two block barriers per step.
+// Runs steps k = 0 .. k_stop-1.  k_stop == d-1: complete reduction (dd[d-1] included).  k_stop < d-1: stops
+// with the rank-2 update of step k_stop-1 still pending in S.vw (rows k_stop..d-1); the caller applies it
+// while handing the trailing block to the next stage (tri_store_trailing).
+template <int NT, int PSTR>
 __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S, float2* tau_out, float* dd,
-                             float* ee) {
+                             float* ee, int k_stop) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < 128) S.vw[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     float2 tau_prev = make_float2(0.f, 0.f);
-    for (int k = 0; k < d; ++k) {
+    const bool partial = k_stop < d - 1;
+    for (int k = 0; k <= k_stop; ++k) {
         const int m = d - k - 1;            // trailing size of step k (m == 0: only the epilogue of step d-2)
+        const bool last = (k == k_stop);
         if (wid == 0) {
             // rows k..d-1 = local rows t = lane + 32 j of step k-1's trailing block
             float2 vr[4], w[4];
             const int mp = m + 1;
             // ---- finish step k-1
             if (k > 0) {
-                const int nq = mp > 32 ? 4 : 8;
+                const int nq = mp > 32 ? NT / 64 : NT / 32;
                 float2 p[4];
                 float dx = 0.f, dy = 0.f;
 #pragma unroll
@@ -116,7 +122,7 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
                     vr[j] = make_float2(0.f, 0.f);
                     if (t < mp) {
                         float2 sacc = make_float2(0.f, 0.f);
-                        for (int qq = 0; qq < nq; ++qq) sacc = cadd(sacc, S.part[qq * 128 + t]);
+                        for (int qq = 0; qq < nq; ++qq) sacc = cadd(sacc, S.part[qq * PSTR + t]);
                         p[j] = cmul(tau_prev, sacc);
                         vr[j] = S.vn[k + t];
                         dx = fmaf(p[j].x, vr[j].x, dx); dx = fmaf(p[j].y, vr[j].y, dx);      // conj(p) * v
@@ -139,6 +145,7 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { vr[j] = make_float2(0.f, 0.f); w[j] = make_float2(0.f, 0.f); }
             }
+            if (!(last && partial)) {
             // pending (v,w) of row k (local row 0: lane 0, slot 0)
             const float vkx = __shfl_sync(0xffffffffu, vr[0].x, 0), vky = __shfl_sync(0xffffffffu, vr[0].y, 0);
             const float wkx = __shfl_sync(0xffffffffu, w[0].x, 0), wky = __shfl_sync(0xffffffffu, w[0].y, 0);
@@ -193,32 +200,53 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
                 }
                 tau_prev = tau;
             }
+            }
         }
-        if (m == 0) break;
+        if (last) break;
         __syncthreads();
         // ---- fused pending update + mat-vec with the new reflector
-        if (m > 64) tri_fused_pass<2, 64>(A, ld, k, m, S);
-        else if (m > 32) tri_fused_pass<1, 64>(A, ld, k, m, S);
-        else tri_fused_pass<1, 32>(A, ld, k, m, S);
+        if (NT == 256 && m > 64) tri_fused_pass<2, 64, NT, PSTR>(A, ld, k, m, S);
+        else if (m > 32) tri_fused_pass<1, 64, NT, PSTR>(A, ld, k, m, S);
+        else tri_fused_pass<1, 32, NT, PSTR>(A, ld, k, m, S);
         __syncthreads();
     }
     __syncthreads();
 }
 
-// Export reflectors (column-concatenated), tau, and the tridiagonal ([i][B] layout for k_ql).
+// Hand the trailing block (rows/cols k0..d-1, pending update applied) to the next stage: full, row-major
+// [d2][d2] in global memory (Hermitian, so row-/column-major only differ by conjugation; we store A[r][c]).
+__device__ void tri_store_trailing(const float2* __restrict__ A, int d, int ld, int k0, const TriScratch& S,
+                                   float2* __restrict__ T) {
+    const int d2 = d - k0;
+    for (int idx = threadIdx.x; idx < d2 * d2; idx += blockDim.x) {
+        const int c = idx / d2, r = idx % d2;            // consecutive threads -> consecutive rows (smem stride 1)
+        float2 x = A[(k0 + r) + (size_t)(k0 + c) * ld];
+        const float4 tr = S.vw[k0 + r], tc = S.vw[k0 + c];
+        x.x = fmaf(-tr.x, tc.z, x.x); x.x = fmaf(-tr.y, tc.w, x.x);
+        x.x = fmaf(-tr.z, tc.x, x.x); x.x = fmaf(-tr.w, tc.y, x.x);
+        x.y = fmaf(-tr.y, tc.z, x.y); x.y = fmaf(tr.x, tc.w, x.y);
+        x.y = fmaf(-tr.w, tc.x, x.y); x.y = fmaf(tr.z, tc.y, x.y);
+        T[(size_t)c * d2 + r] = x;                         // column-major [c][r]
+    }
+}
+
+// Export one stage: reflectors k = 0..nk-1 of the local matrix (order d, global offset k0 inside a matrix of
+// order dg), tau[k], and d/e entries i = 0..ni-1 ([i][B] layout for k_ql).
 __device__ void export_tridiag(const float2* __restrict__ A, int d, int ld, const float2* tau_s, const float* dd,
                                const float* ee, float2* __restrict__ Vg, float2* __restrict__ taug,
-                               float* __restrict__ dT, float* __restrict__ eT, int B, int sig) {
+                               float* __restrict__ dT, float* __restrict__ eT, int B, int sig, int k0, int dg, int nk,
+                               int ni) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    for (int k = wid; k < d - 1; k += nw) {
-        const int off = voff(k, d);
+    for (int k = wid; k < nk; k += nw) {
+        const int off = voff(k0 + k, dg);
         for (int i = k + 1 + lane; i < d; i += 32)
             Vg[off + i - (k + 1)] = (i == k + 1) ? make_float2(1.f, 0.f) : A[i + (size_t)k * ld];
     }
-    for (int i = tid; i < d; i += blockDim.x) {
-        taug[i] = i < d - 1 ? tau_s[i] : make_float2(0.f, 0.f);
-        dT[(size_t)i * B + sig] = dd[i];
-        eT[(size_t)i * B + sig] = i < d - 1 ? ee[i] : 0.f;
+    for (int i = tid; i < ni; i += blockDim.x) {
+        const int gi = k0 + i;
+        taug[gi] = gi < dg - 1 ? tau_s[i] : make_float2(0.f, 0.f);
+        dT[(size_t)gi * B + sig] = dd[i];
+        eT[(size_t)gi * B + sig] = gi < dg - 1 ? ee[i] : 0.f;
     }
 }
 
@@ -284,7 +312,9 @@ struct HeadArgs {
     float2* tau;         // [B][d]
     float* dT;           // [d][B]
     float* eT;           // [d][B]
+    float2* Ttr;         // [B][d2*d2] trailing block handed to k_head2 (k1 < d-1)
     int B, n, d, ld, first;
+    int k1;              // Householder steps done here; d-1 = everything
 };
 
 __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
@@ -398,14 +428,62 @@ __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
     if (tid == 0) s.A[n + (size_t)n * ld].x += P[P_C0];
     __syncthreads();
     // ---- eigh, stage 1
-    tridiag_smem(s.A, d, ld, s.S, s.tau, s.dd, s.ee);
-    export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, GV, a.tau + (size_t)sig * d, a.dT, a.eT, a.B, sig);
+    tridiag_smem<256, 128>(s.A, d, ld, s.S, s.tau, s.dd, s.ee, a.k1);
+    const bool full = a.k1 >= d - 1;
+    export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, GV, a.tau + (size_t)sig * d, a.dT, a.eT, a.B, sig, 0, d,
+                   full ? d - 1 : a.k1, full ? d : a.k1);
+    if (!full) {
+        const int d2 = d - a.k1;
+        tri_store_trailing(s.A, d, ld, a.k1, s.S, a.Ttr + (size_t)sig * d2 * d2);
+    }
+}
+
+// Second stage of the tridiagonalisation: the trailing block of order d2 <= 64 (compacted by k_head) needs
+// 42 KB of shared memory instead of 101 KB, so five CTAs share an SM and hide each other's serial sections.
+struct Head2Args {
+    const float2* Ttr;   // [B][d2*d2] column-major
+    float2* GV;          // [B][npk] reflector store (offsets of the full matrix)
+    float2* tau;         // [B][d]
+    float* dT;
+    float* eT;
+    int B, d, d2, ld2, k1;
+};
+__host__ __device__ inline size_t head2_smem_bytes(int d2, int ld2) {
+    return ((size_t)d2 * ld2 + 1 + 256 + 128 + 512 + 4 + 128) * sizeof(float2) + (128 + 128) * sizeof(float);
+}
+__global__ void __launch_bounds__(128, 5) k_head2(Head2Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d2 = a.d2, ld2 = a.ld2;
+    float2* p2 = reinterpret_cast<float2*>(smem_raw);
+    float2* A = p2; p2 += (size_t)d2 * ld2;
+    p2 += ((size_t)d2 * ld2) & 1;
+    TriScratch S;
+    S.vw = reinterpret_cast<float4*>(p2); p2 += 256;
+    S.vn = p2; p2 += 128;
+    S.part = p2; p2 += 512;
+    S.scal = p2; p2 += 4;
+    float2* tau_s = p2; p2 += 128;
+    float* dd = reinterpret_cast<float*>(p2);
+    float* ee = dd + 128;
+    S.red = nullptr;
+    const int sig = blockIdx.x;
+    const float2* T = a.Ttr + (size_t)sig * d2 * d2;
+    for (int idx = threadIdx.x; idx < d2 * d2; idx += 128) {
+        const int c = idx / d2, r = idx % d2;
+        A[r + (size_t)c * ld2] = T[idx];
+    }
+    __syncthreads();
+    tridiag_smem<128, 64>(A, d2, ld2, S, tau_s, dd, ee, d2 - 1);
+    const int npk = a.d * (a.d + 1) / 2;
+    export_tridiag(A, d2, ld2, tau_s, dd, ee, a.GV + (size_t)sig * npk, a.tau + (size_t)sig * a.d, a.dT, a.eT, a.B, sig,
+                   a.k1, a.d, d2 - 1, d2);
 }
 
 // Debug/unit entry: tridiagonalise arbitrary Hermitian matrices given as full row-major [B][d][d]
 // (lower triangle is read).
 __global__ void __launch_bounds__(256, 2)
-k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, float2* tau, float* dT, float* eT) {
+k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, float2* tau, float* dT, float* eT,
+          float2* Ttr, int k1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeadSmem s = carve_head(smem_raw, d, ld);
     const int sig = blockIdx.x;
@@ -421,8 +499,14 @@ k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, flo
         }
     }
     __syncthreads();
-    tridiag_smem(s.A, d, ld, s.S, s.tau, s.dd, s.ee);
-    export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, V + (size_t)sig * npk, tau + (size_t)sig * d, dT, eT, B, sig);
+    tridiag_smem<256, 128>(s.A, d, ld, s.S, s.tau, s.dd, s.ee, k1);
+    const bool full = k1 >= d - 1;
+    export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, V + (size_t)sig * npk, tau + (size_t)sig * d, dT, eT, B, sig, 0, d,
+                   full ? d - 1 : k1, full ? d : k1);
+    if (!full) {
+        const int d2 = d - k1;
+        tri_store_trailing(s.A, d, ld, k1, s.S, Ttr + (size_t)sig * d2 * d2);
+    }
 }
 
 // =====================================================================================
