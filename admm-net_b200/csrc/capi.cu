@@ -101,8 +101,15 @@ struct Ws {
 };
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int NSLOT = 2;
-constexpr int TR_MAX = 64;   // order of the trailing block handed to the second tridiagonalisation stage
-inline int stage1_steps(int d) { return d > TR_MAX + 8 ? d - TR_MAX : d - 1; }
+constexpr int TR_MAX = 80;   // largest trailing block handed to a later tridiagonalisation stage
+// orders at which the trailing block is compacted and handed to the next (smaller, higher-occupancy) stage
+inline int next_stage_order(int d) {
+    const int marks[3] = {80, 64, 40};
+    for (int i = 0; i < 3; ++i)
+        if (d > marks[i] + 8) return marks[i];
+    return 0;     // finish in this stage
+}
+inline int stage1_steps(int d) { const int nx = next_stage_order(d); return nx ? d - nx : d - 1; }
 inline int default_rcap(int d) { return ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
 
 // n = signal length (for phi/h), d = matrix order.  Per-signal STATE arrays (Zp, GV, phi_cur, h_cur, r) cover
@@ -119,7 +126,7 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     w.Zr = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
     w.rot = (float2*)take((size_t)NSLOT * C * rcap * sizeof(float2));
     w.tau = (float2*)take((size_t)NSLOT * C * d * sizeof(float2));
-    w.Ttr = (float2*)take((size_t)NSLOT * C * TR_MAX * TR_MAX * sizeof(float2));
+    w.Ttr = (float2*)take((size_t)NSLOT * C * 2 * TR_MAX * TR_MAX * sizeof(float2));   // ping-pong pair per slot
     w.lam = (float*)take((size_t)NSLOT * C * d * sizeof(float));
     w.dT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
     w.eT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
@@ -143,18 +150,32 @@ int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
     return 0;
 }
 
-// second tridiagonalisation stage on the compacted trailing block (no-op when stage 1 did everything)
+// later tridiagonalisation stages on the compacted trailing block (no-op when stage 1 did everything)
 int launch_head2(const Ws& w, int B, int d, cudaStream_t st) {
-    const int k1 = stage1_steps(d);
-    if (k1 >= d - 1) return 0;
-    Head2Args h;
-    h.Ttr = w.Ttr; h.GV = w.GV; h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
-    h.B = B; h.d = d; h.d2 = d - k1; h.ld2 = h.d2 | 1; h.k1 = k1;
-    const size_t sm = head2_smem_bytes(h.d2, h.ld2);
-    CK(cudaFuncSetAttribute(k_head2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    prof::Scope pscope(prof::HEAD2, st);
-    k_head2<<<B, 128, sm, st>>>(h);
-    CK(cudaGetLastError());
+    int dcur = next_stage_order(d);          // order handed over by k_head
+    if (!dcur) return 0;
+    const size_t tr_sz = (size_t)B * TR_MAX * TR_MAX;
+    float2* bufs[2] = {w.Ttr, w.Ttr + tr_sz};
+    int which = 0;
+    while (dcur) {
+        const int nx = next_stage_order(dcur);
+        Head2Args h;
+        h.Tin = bufs[which]; h.Tout = bufs[which ^ 1]; h.GV = w.GV; h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
+        h.B = B; h.d = d; h.d2 = dcur; h.ld2 = dcur | 1; h.k0 = d - dcur; h.k_stop = nx ? dcur - nx : dcur - 1;
+        prof::Scope pscope(prof::HEAD2, st);
+        if (dcur > 64) {
+            const size_t sm = head2_smem_bytes<256, 128>(h.d2, h.ld2);
+            CK(cudaFuncSetAttribute(k_head2<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_head2<256, 128><<<B, 256, sm, st>>>(h);
+        } else {
+            const size_t sm = head2_smem_bytes<128, 64>(h.d2, h.ld2);
+            CK(cudaFuncSetAttribute(k_head2<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_head2<128, 64><<<B, 128, sm, st>>>(h);
+        }
+        CK(cudaGetLastError());
+        which ^= 1;
+        dcur = nx;
+    }
     return 0;
 }
 
@@ -215,7 +236,7 @@ static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0
     c.Zr += (size_t)slot * C * d * d;
     c.rot += (size_t)slot * C * rcap;
     c.tau += (size_t)slot * C * d;
-    c.Ttr += (size_t)slot * C * TR_MAX * TR_MAX;
+    c.Ttr += (size_t)slot * C * 2 * TR_MAX * TR_MAX;
     c.lam += (size_t)slot * C * d;
     c.dT += (size_t)slot * C * d;
     c.eT += (size_t)slot * C * d;

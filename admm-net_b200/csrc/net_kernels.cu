@@ -112,7 +112,7 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
             const int mp = m + 1;
             // ---- finish step k-1
             if (k > 0) {
-                const int nq = mp > 32 ? NT / 64 : NT / 32;
+                const int nq = mp > 32 ? NT / 64 : NT / 32;     // column groups of the pass that produced `part`
                 float2 p[4];
                 float dx = 0.f, dy = 0.f;
 #pragma unroll
@@ -205,7 +205,7 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
         if (last) break;
         __syncthreads();
         // ---- fused pending update + mat-vec with the new reflector
-        if (NT == 256 && m > 64) tri_fused_pass<2, 64, NT, PSTR>(A, ld, k, m, S);
+        if (PSTR > 64 && m > 64) tri_fused_pass<2, 64, NT, PSTR>(A, ld, k, m, S);
         else if (m > 32) tri_fused_pass<1, 64, NT, PSTR>(A, ld, k, m, S);
         else tri_fused_pass<1, 32, NT, PSTR>(A, ld, k, m, S);
         __syncthreads();
@@ -438,20 +438,24 @@ __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
     }
 }
 
-// Second stage of the tridiagonalisation: the trailing block of order d2 <= 64 (compacted by k_head) needs
-// 42 KB of shared memory instead of 101 KB, so five CTAs share an SM and hide each other's serial sections.
+// Later stages of the tridiagonalisation: the trailing block (order d2 <= 80, compacted by the previous
+// stage) needs far less shared memory than the full matrix (62 / 42 / 24 KB at d2 = 80 / 60 / 40 against
+// 101 KB), so 3 / 5 / 8 CTAs share an SM and hide each other's serial sections and barriers.
 struct Head2Args {
-    const float2* Ttr;   // [B][d2*d2] column-major
+    const float2* Tin;   // [B][d2*d2] column-major trailing block from the previous stage
+    float2* Tout;        // [B][d3*d3] trailing block for the next stage (k_stop < d2-1)
     float2* GV;          // [B][npk] reflector store (offsets of the full matrix)
     float2* tau;         // [B][d]
     float* dT;
     float* eT;
-    int B, d, d2, ld2, k1;
+    int B, d, d2, ld2, k0, k_stop;
 };
+template <int NT, int PSTR>
 __host__ __device__ inline size_t head2_smem_bytes(int d2, int ld2) {
-    return ((size_t)d2 * ld2 + 1 + 256 + 128 + 512 + 4 + 128) * sizeof(float2) + (128 + 128) * sizeof(float);
+    return ((size_t)d2 * ld2 + 1 + 256 + 128 + (NT / 32) * PSTR + 4 + 128) * sizeof(float2) + (128 + 128) * sizeof(float);
 }
-__global__ void __launch_bounds__(128, 5) k_head2(Head2Args a) {
+template <int NT, int PSTR>
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : 3) k_head2(Head2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int d2 = a.d2, ld2 = a.ld2;
     float2* p2 = reinterpret_cast<float2*>(smem_raw);
@@ -460,23 +464,28 @@ __global__ void __launch_bounds__(128, 5) k_head2(Head2Args a) {
     TriScratch S;
     S.vw = reinterpret_cast<float4*>(p2); p2 += 256;
     S.vn = p2; p2 += 128;
-    S.part = p2; p2 += 512;
+    S.part = p2; p2 += (NT / 32) * PSTR;
     S.scal = p2; p2 += 4;
     float2* tau_s = p2; p2 += 128;
     float* dd = reinterpret_cast<float*>(p2);
     float* ee = dd + 128;
     S.red = nullptr;
     const int sig = blockIdx.x;
-    const float2* T = a.Ttr + (size_t)sig * d2 * d2;
-    for (int idx = threadIdx.x; idx < d2 * d2; idx += 128) {
+    const float2* T = a.Tin + (size_t)sig * d2 * d2;
+    for (int idx = threadIdx.x; idx < d2 * d2; idx += NT) {
         const int c = idx / d2, r = idx % d2;
         A[r + (size_t)c * ld2] = T[idx];
     }
     __syncthreads();
-    tridiag_smem<128, 64>(A, d2, ld2, S, tau_s, dd, ee, d2 - 1);
+    tridiag_smem<NT, PSTR>(A, d2, ld2, S, tau_s, dd, ee, a.k_stop);
     const int npk = a.d * (a.d + 1) / 2;
+    const bool full = a.k_stop >= d2 - 1;
     export_tridiag(A, d2, ld2, tau_s, dd, ee, a.GV + (size_t)sig * npk, a.tau + (size_t)sig * a.d, a.dT, a.eT, a.B, sig,
-                   a.k1, a.d, d2 - 1, d2);
+                   a.k0, a.d, full ? d2 - 1 : a.k_stop, full ? d2 : a.k_stop);
+    if (!full) {
+        const int d3 = d2 - a.k_stop;
+        tri_store_trailing(A, d2, ld2, a.k_stop, S, a.Tout + (size_t)sig * d3 * d3);
+    }
 }
 
 // Debug/unit entry: tridiagonalise arbitrary Hermitian matrices given as full row-major [B][d][d]
