@@ -348,11 +348,24 @@ __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
     } else {
         const float alpha = z_alpha(a.Pkm1, a.r_prev[sig], *a.mean_prev);
         const float c1z = a.Pkm1[P_C1Z];
-        for (int i = wid; i < d; i += 8) {
-            for (int j = lane; j <= i; j += 32) {
-                const int idx = pk(i, j);
-                float2 z = Zp[idx];
-                const float2 g = GV[idx];
+        // flat, coalesced sweep over the packed triangles; 4 independent loads in flight per thread
+        for (int base = 0; base < npk; base += 4 * 256) {
+            float2 zv[4], gv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 256 + tid;
+                if (idx < npk) { zv[u] = Zp[idx]; gv[u] = GV[idx]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 256 + tid;
+                if (idx >= npk) continue;
+                int i = (int)((sqrtf(8.f * (float)idx + 1.f) - 1.f) * 0.5f);      // row of packed index
+                while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+                while (i * (i + 1) / 2 > idx) --i;
+                const int j = idx - i * (i + 1) / 2;
+                float2 z = zv[u];
+                const float2 g = gv[u];
                 float2 c = make_float2(0.f, 0.f);
                 if (i == j) c.x = (i < n) ? s.hp[i] : c1z;
                 else if (i == n) c = cconj(s.phip[j]);
