@@ -101,11 +101,11 @@ struct Ws {
 };
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int NSLOT = 2;
-constexpr int TR_MAX = 80;   // largest trailing block handed to a later tridiagonalisation stage
+constexpr int TR_MAX = 88;   // largest trailing block handed to a later tridiagonalisation stage
 // orders at which the trailing block is compacted and handed to the next (smaller, higher-occupancy) stage
 inline int next_stage_order(int d) {
-    const int marks[3] = {80, 64, 40};
-    for (int i = 0; i < 3; ++i)
+    const int marks[4] = {88, 72, 56, 40};
+    for (int i = 0; i < 4; ++i)
         if (d > marks[i] + 8) return marks[i];
     return 0;     // finish in this stage
 }

@@ -55,8 +55,38 @@ __device__ __forceinline__ void tri_fused_pass(float2* __restrict__ A, int ld, i
     }
     if (on[0]) {
         float2* a0 = A + (g0 + rr) + (size_t)g0 * ld;
-#pragma unroll 2
-        for (int c = q; c < m; c += NQ) {
+        // CU columns per trip: all shared-memory loads first, then the FMA chains, then the stores
+        constexpr int CU = NROWS >= 3 ? 2 : 4;
+        int c = q;
+        for (; c + (CU - 1) * NQ < m; c += CU * NQ) {
+            float4 t[CU];
+            float2 vn[CU], x[CU][NROWS];
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                t[u] = S.vw[g0 + c + u * NQ];
+                vn[u] = S.vn[g0 + c + u * NQ];
+#pragma unroll
+                for (int i = 0; i < NROWS; ++i)
+                    if (i == 0 || on[i]) x[u][i] = a0[i * RSTRIDE + (size_t)(c + u * NQ) * ld];
+            }
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+#pragma unroll
+                for (int i = 0; i < NROWS; ++i) {
+                    if (i == 0 || on[i]) {
+                        float2 xx = x[u][i];
+                        xx.x = fmaf(-vo[i].x, t[u].z, xx.x); xx.x = fmaf(-vo[i].y, t[u].w, xx.x);
+                        xx.x = fmaf(-wo[i].x, t[u].x, xx.x); xx.x = fmaf(-wo[i].y, t[u].y, xx.x);
+                        xx.y = fmaf(-vo[i].y, t[u].z, xx.y); xx.y = fmaf(vo[i].x, t[u].w, xx.y);
+                        xx.y = fmaf(-wo[i].y, t[u].x, xx.y); xx.y = fmaf(wo[i].x, t[u].y, xx.y);
+                        a0[i * RSTRIDE + (size_t)(c + u * NQ) * ld] = xx;
+                        acc[i].x = fmaf(xx.x, vn[u].x, acc[i].x); acc[i].x = fmaf(-xx.y, vn[u].y, acc[i].x);
+                        acc[i].y = fmaf(xx.x, vn[u].y, acc[i].y); acc[i].y = fmaf(xx.y, vn[u].x, acc[i].y);
+                    }
+                }
+            }
+        }
+        for (; c < m; c += NQ) {
             const float4 t = S.vw[g0 + c];
             const float2 vn = S.vn[g0 + c];
 #pragma unroll
@@ -112,7 +142,7 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
             const int mp = m + 1;
             // ---- finish step k-1
             if (k > 0) {
-                const int nq = mp > 32 ? NT / 64 : NT / 32;     // column groups of the pass that produced `part`
+                constexpr int nq = NT / 32;                     // column groups of the pass that produced `part`
                 float2 p[4];
                 float dx = 0.f, dy = 0.f;
 #pragma unroll
@@ -122,6 +152,7 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
                     vr[j] = make_float2(0.f, 0.f);
                     if (t < mp) {
                         float2 sacc = make_float2(0.f, 0.f);
+#pragma unroll
                         for (int qq = 0; qq < nq; ++qq) sacc = cadd(sacc, S.part[qq * PSTR + t]);
                         p[j] = cmul(tau_prev, sacc);
                         vr[j] = S.vn[k + t];
@@ -205,8 +236,10 @@ __device__ void tridiag_smem(float2* __restrict__ A, int d, int ld, TriScratch S
         if (last) break;
         __syncthreads();
         // ---- fused pending update + mat-vec with the new reflector
-        if (PSTR > 64 && m > 64) tri_fused_pass<2, 64, NT, PSTR>(A, ld, k, m, S);
-        else if (m > 32) tri_fused_pass<1, 64, NT, PSTR>(A, ld, k, m, S);
+        // rows -> lanes in stripes of 32 (at most 31 idle lanes), NT/32 column groups
+        if (PSTR > 96 && m > 96) tri_fused_pass<4, 32, NT, PSTR>(A, ld, k, m, S);
+        else if (PSTR > 64 && m > 64) tri_fused_pass<3, 32, NT, PSTR>(A, ld, k, m, S);
+        else if (m > 32) tri_fused_pass<2, 32, NT, PSTR>(A, ld, k, m, S);
         else tri_fused_pass<1, 32, NT, PSTR>(A, ld, k, m, S);
         __syncthreads();
     }
@@ -321,7 +354,7 @@ __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, d = a.d, ld = a.ld;
     HeadSmem s = carve_head(smem_raw, d, ld);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const int sig = blockIdx.x;
     const int npk = d * (d + 1) / 2;
     const float* __restrict__ P = a.Pk;
