@@ -28,8 +28,8 @@ static int fail(int code, const std::string& msg) {
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
 // Process-global, not thread safe; off by default (then the only cost is one branch per launch).
 namespace prof {
-enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, NKINDS };
-static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2"};
+enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, NKINDS };
+static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge"};
 struct Rec { int kind; cudaEvent_t a, b; };
 static bool on = false;
 static std::vector<Rec> recs;
@@ -94,7 +94,8 @@ extern "C" int admmnet_param_stride(int n) { return param_stride(n); }
 namespace {
 struct Ws {
     float2 *Zp, *GV, *rot, *tau, *phi_cur, *Ttr;
-    float *Zr, *lam, *dT, *eT, *h_cur, *r, *mean;
+    float *Zr, *Zr2, *lam, *dT, *eT, *h_cur, *r, *mean;
+    double* rho;
     int *nrot, *status;
     double* rsum;
     size_t bytes;
@@ -104,9 +105,22 @@ constexpr int NSLOT = 2;
 constexpr int TR_MAX = 88;   // largest trailing block handed to a later tridiagonalisation stage
 // orders at which the trailing block is compacted and handed to the next (smaller, higher-occupancy) stage
 inline int next_stage_order(int d) {
-    const int marks[4] = {88, 72, 56, 40};
-    for (int i = 0; i < 4; ++i)
-        if (d > marks[i] + 8) return marks[i];
+    static int marks[8] = {88, 72, 56, 40, 0, 0, 0, 0};
+    static bool init = false;
+    if (!init) {                                   // ADMMNET_STAGES="88,72,56,40" overrides the plan (tuning)
+        init = true;
+        if (const char* e = getenv("ADMMNET_STAGES")) {
+            int n = 0;
+            for (const char* p = e; *p && n < 7;) {
+                marks[n++] = atoi(p);
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
+            }
+            for (; n < 8; ++n) marks[n] = 0;
+        }
+    }
+    for (int i = 0; i < 8 && marks[i] > 0; ++i)
+        if (marks[i] <= TR_MAX && d > marks[i] + 8) return marks[i];
     return 0;     // finish in this stage
 }
 inline int stage1_steps(int d) { const int nx = next_stage_order(d); return nx ? d - nx : d - 1; }
@@ -124,6 +138,8 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     w.GV = (float2*)take(B * npk * sizeof(float2));
     // two scratch slots so that consecutive chunks can be in flight on different streams
     w.Zr = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
+    w.Zr2 = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
+    w.rho = (double*)take((size_t)NSLOT * C * DC_MAXTEAR * sizeof(double));
     w.rot = (float2*)take((size_t)NSLOT * C * rcap * sizeof(float2));
     w.tau = (float2*)take((size_t)NSLOT * C * d * sizeof(float2));
     w.Ttr = (float2*)take((size_t)NSLOT * C * 2 * TR_MAX * TR_MAX * sizeof(float2));   // ping-pong pair per slot
@@ -148,6 +164,24 @@ int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
     if (rcap == 0) rcap = default_rcap(n + 1);
     if (rcap < 2048 || rcap % ROT_CHUNK) return fail(ADMMNET_ERR_ARG, "rcap must be a multiple of 1024, >= 2048");
     return 0;
+}
+
+// Divide & conquer plan for the tridiagonal eigenproblem: L levels -> 2^L blocks (ADMMNET_DC=L, default 0 = plain
+// QL).  Measured on B200 (131072 signals x 9 layers): L=3 cuts k_ql 292 -> 85 ms and k_rot 468 -> 157 ms per step, but
+// the fp64-flavoured secular solves of k_merge cost 1690 ms, so the path is validated (all parity tests pass with
+// ADMMNET_DC=1..3) but off by default until the merge is rewritten in fp32 with Loewner-corrected z.
+inline int dc_levels(int d) {
+    static const int env = getenv("ADMMNET_DC") ? atoi(getenv("ADMMNET_DC")) : 0;
+    int L = env < 0 ? 0 : (env > 3 ? 3 : env);
+    while (L > 0 && (d >> L) < 8) --L;        // blocks of at least 8
+    return L;
+}
+inline TearSpec dc_tears(int d) {
+    TearSpec ts;
+    const int L = dc_levels(d), nb = 1 << L;
+    ts.n = nb - 1;
+    for (int q = 0; q < ts.n; ++q) ts.pos[q] = (int)(((long long)(q + 1) * d) / nb);
+    return ts;
 }
 
 // later tridiagonalisation stages on the compacted trailing block (no-op when stage 1 did everything)
@@ -195,7 +229,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
-                                                                         status);
+                                                                         status, dc_tears(d), w.rho);
         CK(cudaGetLastError());
     }
     if (side) {
@@ -209,9 +243,41 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr);
         CK(cudaGetLastError());
     }
+    // divide & conquer merges, leaves -> root; Z ping-pongs between the two scratch buffers
+    const float* zfinal = w.Zr;
+    {
+        const TearSpec ts = dc_tears(d);
+        const int L = dc_levels(d);
+        float* zb[2] = {w.Zr, w.Zr2};
+        int cur = 0;
+        for (int lev = 1; lev <= L; ++lev) {
+            const int half = 1 << (lev - 1), step = 1 << lev;
+            // tears handled at this level: 1-based number t with t % step == half; its range is bounded by the
+            // tears t-half and t+half.  The ranges of a level partition [0,d): one launch handles all (<= 4).
+            MergeArgs m;
+            m.Zin = zb[cur]; m.Zout = zb[cur ^ 1]; m.lam = w.lam; m.rho = w.rho; m.status = status;
+            m.B = B; m.d = d; m.nr = 0;
+            for (int i = 0; i < ts.n; ++i) {
+                if ((i + 1) % step != half) continue;
+                const int lo = (i + 1) - half, hi = (i + 1) + half;
+                m.ra[m.nr] = lo == 0 ? 0 : ts.pos[lo - 1];
+                m.rb[m.nr] = hi > ts.n ? d : ts.pos[hi - 1];
+                m.rp[m.nr] = ts.pos[i];
+                m.rt[m.nr] = i;
+                ++m.nr;
+            }
+            const size_t smm = merge_smem_bytes(d);
+            CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm));
+            prof::Scope pscope(prof::MERGE, st);
+            k_merge<<<B, MG_THREADS, smm, st>>>(m);
+            CK(cudaGetLastError());
+            cur ^= 1;
+        }
+        zfinal = zb[cur];
+    }
     {
         TailArgs t;
-        t.Zr = w.Zr; t.GV = w.GV; t.tau = w.tau; t.lam = w.lam; t.phi_cur = w.phi_cur; t.h_cur = w.h_cur;
+        t.Zr = zfinal; t.GV = w.GV; t.tau = w.tau; t.lam = w.lam; t.phi_cur = w.phi_cur; t.h_cur = w.h_cur;
         t.Pk = Pk; t.r_out = w.r; t.U_out = U_out; t.lamp_out = lamp_out;
         t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c;
         const size_t sm = tail_smem_bytes(d, t.ldu);
@@ -234,6 +300,8 @@ static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0
     Ws c = w;
     const size_t npk = (size_t)d * (d + 1) / 2;
     c.Zr += (size_t)slot * C * d * d;
+    c.Zr2 += (size_t)slot * C * d * d;
+    c.rho += (size_t)slot * C * DC_MAXTEAR;
     c.rot += (size_t)slot * C * rcap;
     c.tau += (size_t)slot * C * d;
     c.Ttr += (size_t)slot * C * 2 * TR_MAX * TR_MAX;

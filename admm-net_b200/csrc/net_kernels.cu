@@ -580,9 +580,18 @@ k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, flo
 // sweep (every off-diagonal of the active block is rewritten by the sweep, so the smallest negligible
 // index is known when the sweep ends); a scan is only needed at the start and in the rare case of
 // three simultaneous deflations.
+// Divide & conquer support: the tridiagonal is torn at `ntear` rows p (Cuppen): T = diag(T1', T2') + rho v v^T,
+// rho = e[p-1], d[p-1] -= rho, d[p] -= rho, e[p-1] = 0.  QL then works on the independent blocks (its sweeps
+// are ~1/nblocks as long), and k_merge glues the blocks back with secular-equation solves + a small GEMM.
+#define DC_MAXTEAR 7
+struct TearSpec {
+    int n;
+    int pos[DC_MAXTEAR];
+};
 __global__ void __launch_bounds__(QL_THREADS)
 k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, float* __restrict__ lam,
-     float2* __restrict__ rot, int rcap, int* __restrict__ nrot, int* __restrict__ status) {
+     float2* __restrict__ rot, int rcap, int* __restrict__ nrot, int* __restrict__ status, TearSpec tears,
+     double* __restrict__ rho_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sd = reinterpret_cast<double*>(smem_raw);
     double* se = sd + (size_t)d * QL_THREADS;
@@ -597,6 +606,14 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
         D_(i) = di;
         E_(i) = ei;
         anorm = fmax(anorm, fmax(fabs(di), fabs(ei)));
+    }
+    for (int q = 0; q < tears.n; ++q) {
+        const int p = tears.pos[q];
+        const double rho = E_(p - 1);
+        D_(p - 1) -= rho;
+        D_(p) -= rho;
+        E_(p - 1) = 0.0;
+        if (valid) rho_out[(size_t)sig * DC_MAXTEAR + q] = rho;
     }
     const double eps = 3.0e-8, floor_abs = 1.0e-9 * anorm;
     float2* out = rot + (size_t)(valid ? sig : 0) * rcap;
@@ -825,6 +842,369 @@ k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, in
     __syncwarp();
     float* outz = Zt + (size_t)sig * d * d;
     for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldr + (idx % d)];
+}
+
+// =====================================================================================
+// k_merge: one level of the divide & conquer merge tree.  Every range [a,b) of the level is the union of two
+// already-solved blocks torn at row p; eigenpairs of diag(D) + rho z z^T (z = Q^T v, poles D = block eigenvalues
+// rounded to fp32 so that pole differences are exact in fp64) come from the secular equation
+//     1 + rho * sum_i z_i^2 / (d_i - lambda) = 0
+// solved in fp64 in coordinates shifted to the nearer pole (safeguarded Newton), and the new eigenvectors are
+// Q * W with W_ij = z_i / (d_i - lambda_j), a small fp32 GEMM.  Deflation: |z_i| negligible -> pair kept;
+// exactly equal poles -> Givens rotation of the two columns.  One CTA per signal; Zt is Z^T ([c][r]).
+// =====================================================================================
+#define MG_THREADS 256
+#define MG_MAXR 4
+struct MergeArgs {
+    const float* Zin;     // [B][d][d]
+    float* Zout;          // [B][d][d]
+    float* lam;           // [B][d] in/out
+    const double* rho;    // [B][DC_MAXTEAR]
+    int* status;
+    int B, d, nr;
+    int ra[MG_MAXR], rp[MG_MAXR], rb[MG_MAXR], rt[MG_MAXR];   // range [a,b), tear row p, tear index
+};
+__host__ __device__ inline size_t merge_smem_bytes(int d) {
+    const int ldr = 4 * ((d + 3) / 4);
+    return (size_t)2 * d * ldr * sizeof(float) + (size_t)8 * 128 * sizeof(double) + (size_t)8 * 128 * sizeof(int) + 256;   // (see carve in k_merge)
+}
+
+// Secular function pieces evaluated by a PAIR of lanes (lane parity `par` takes every other term, results combined
+// with one shuffle): psi = sum_{i<=u} z_i^2/((d_i-org)-mu), phi = sum_{i>u}, and their derivatives.  T = float for
+// the bulk of the iteration (the pole differences are still formed in fp64, then rounded), T = double for the polish.
+struct SecVal { double psi, dpsi, phi, dphi; };
+__device__ __forceinline__ float sec_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double sec_rcp(double x) {
+    // 1/x: fp32 seed + two Newton steps (2^-23 -> 2^-46 -> below 2^-53); |x| stays well inside the fp32 range here
+    // except next to a pole, where the plain division is used
+    if (fabs(x) > 1e-30 && fabs(x) < 1e30) {
+        double y = (double)__frcp_rn((float)x);
+        y = y * (2.0 - x * y);
+        y = y * (2.0 - x * y);
+        return y;
+    }
+    return 1.0 / x;
+}
+template <typename T>
+__device__ __forceinline__ SecVal secular_eval(const double* __restrict__ ksd, const double* __restrict__ ksz2, int k, int u,
+                                               double org, double mu, int par) {
+    T p0 = 0, p1 = 0, q0 = 0, q1 = 0;
+    const int nl = k > 0 ? u + 1 : 0;
+    int i = par;
+    for (; i + 2 < nl; i += 4) {
+        const T r0 = sec_rcp((T)((ksd[i] - org) - mu)), r1 = sec_rcp((T)((ksd[i + 2] - org) - mu));
+        const T t0 = (T)ksz2[i] * r0, t1 = (T)ksz2[i + 2] * r1;
+        p0 += t0; p1 += t1;
+        q0 += t0 * r0; q1 += t1 * r1;
+    }
+    for (; i < nl; i += 2) {
+        const T r0 = sec_rcp((T)((ksd[i] - org) - mu));
+        const T t0 = (T)ksz2[i] * r0;
+        p0 += t0; q0 += t0 * r0;
+    }
+    T f0 = 0, f1 = 0, g0 = 0, g1 = 0;
+    for (; i + 2 < k; i += 4) {
+        const T r0 = sec_rcp((T)((ksd[i] - org) - mu)), r1 = sec_rcp((T)((ksd[i + 2] - org) - mu));
+        const T t0 = (T)ksz2[i] * r0, t1 = (T)ksz2[i + 2] * r1;
+        f0 += t0; f1 += t1;
+        g0 += t0 * r0; g1 += t1 * r1;
+    }
+    for (; i < k; i += 2) {
+        const T r0 = sec_rcp((T)((ksd[i] - org) - mu));
+        const T t0 = (T)ksz2[i] * r0;
+        f0 += t0; g0 += t0 * r0;
+    }
+    SecVal v;
+    v.psi = (double)(p0 + p1); v.dpsi = (double)(q0 + q1); v.phi = (double)(f0 + f1); v.dphi = (double)(g0 + g1);
+    v.psi += __shfl_xor_sync(0xffffffffu, v.psi, 1);
+    v.dpsi += __shfl_xor_sync(0xffffffffu, v.dpsi, 1);
+    v.phi += __shfl_xor_sync(0xffffffffu, v.phi, 1);
+    v.dphi += __shfl_xor_sync(0xffffffffu, v.dphi, 1);
+    return v;
+}
+// One step of the two-pole rational interpolation (Bunch-Nielsen-Sorensen; what LAPACK's xLAED4 iterates): psi is
+// modelled by a + s/(dl-x), phi by b + S/(dr-x), matching value and slope at mu; the model's root in (dl,dr) is
+// the next iterate (monotone, quadratic).  `lastroot`: no pole to the right, one-pole model.
+__device__ __forceinline__ double secular_step(const SecVal& v, double rho, double f, double mu, double dl, double dr,
+                                               bool lastroot) {
+    const double Dl = dl - mu, Dr = dr - mu;
+    if (lastroot) {
+        const double s = rho * v.dpsi * Dl * Dl, c0 = f - rho * v.dpsi * Dl;
+        return Dl + s / c0;
+    }
+    const double s = rho * v.dpsi * Dl * Dl, S = rho * v.dphi * Dr * Dr;
+    const double c0 = f - rho * v.dpsi * Dl - rho * v.dphi * Dr;
+    const double A = c0, Bq = c0 * (Dl + Dr) + s + S, Cq = Dl * Dr * f;
+    double disc = Bq * Bq - 4.0 * A * Cq;
+    disc = disc > 0.0 ? sqrt(disc) : 0.0;
+    if (A == 0.0) return Cq / Bq;
+    return Bq > 0.0 ? 2.0 * Cq / (Bq + disc) : (Bq - disc) / (2.0 * A);
+}
+
+__global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d = a.d, ldr = 4 * ((d + 3) / 4);
+    float* Zs = reinterpret_cast<float*>(smem_raw);                 // [d][ldr]  Z^T
+    float* Ws = Zs + (size_t)d * ldr;                               // [d][ldr]  block-diagonal W, Ws[u][t]
+    double* dbl = reinterpret_cast<double*>(Ws + (size_t)d * ldr);
+    double* sd = dbl;             // [128] sorted poles
+    double* sz = dbl + 128;       // [128] sorted z
+    double* ksd = dbl + 256;      // [128] compact (non-deflated) poles
+    double* ksz = dbl + 384;      // [128] compact z
+    double* kmu = dbl + 512;      // [128] root offset from its origin pole
+    double* korg = dbl + 640;     // [128] origin pole value of each root
+    double* kwin = dbl + 768;     // [128] 1/||w||
+    double* rsc = dbl + 896;      // [128] per-range scalars: rho_eff[4], sign[4]
+    int* ib = reinterpret_cast<int*>(dbl + 1024);
+    int* perm = ib;               // [128] sorted position -> original column
+    int* kcol = ib + 128;         // [128] compact index -> original column
+    int* kcnt = ib + 256;         // [MG_MAXR] non-deflated count per range
+    int* rotl = ib + 384;         // [128][2] Givens column pairs
+    float* rotcs = reinterpret_cast<float*>(ib + 640);   // [128][2]
+    int* nrotl = ib + 896;        // [1]
+    const int tid = threadIdx.x;
+    const int sig = blockIdx.x;
+    const float* Zg = a.Zin + (size_t)sig * d * d;
+    float* Zo = a.Zout + (size_t)sig * d * d;
+    float* lam = a.lam + (size_t)sig * d;
+
+    for (int idx = tid; idx < d * d; idx += MG_THREADS) Zs[(idx / d) * ldr + (idx % d)] = Zg[idx];
+    for (int idx = tid; idx < d * ldr; idx += MG_THREADS) Ws[idx] = 0.f;
+    if (tid == 0) *nrotl = 0;
+    __syncthreads();
+    // range of every index
+    int myr = -1;
+    if (tid < d)
+        for (int r = 0; r < a.nr; ++r)
+            if (tid >= a.ra[r] && tid < a.rb[r]) myr = r;
+    // ---- z = Q^T v: row p-1 plus row p of Q (Zs[c][r] = Q[r][c])
+    double zi = 0.0, di = 0.0;
+    if (myr >= 0) {
+        const int p = a.rp[myr];
+        zi = (double)Zs[tid * ldr + p - 1] + (double)Zs[tid * ldr + p];
+        di = (double)lam[tid];
+        kmu[tid] = zi;                 // scratch: unsorted z
+    }
+    __syncthreads();
+    if (tid < a.nr) {
+        double n2 = 0.0;
+        for (int i = a.ra[tid]; i < a.rb[tid]; ++i) n2 += kmu[i] * kmu[i];
+        const double rho = a.rho[(size_t)sig * DC_MAXTEAR + a.rt[tid]] * n2;
+        rsc[tid] = fabs(rho);
+        rsc[4 + tid] = rho < 0.0 ? -1.0 : 1.0;
+        rsc[8 + tid] = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+    }
+    __syncthreads();
+    if (myr >= 0) {
+        zi *= rsc[8 + myr];
+        di *= rsc[4 + myr];            // rho < 0: solve for -T
+        korg[tid] = di;                // scratch: unsorted signed poles
+        kmu[tid] = zi;
+    }
+    __syncthreads();
+    // ---- rank sort inside each range
+    if (myr >= 0) {
+        int rank = a.ra[myr];
+        for (int j = a.ra[myr]; j < a.rb[myr]; ++j) {
+            const double dj = korg[j];
+            rank += (dj < di || (dj == di && j < tid)) ? 1 : 0;
+        }
+        sd[rank] = di;
+        sz[rank] = zi;
+        perm[rank] = tid;
+    }
+    __syncthreads();
+    // ---- deflation scan, one thread per range (serial; rotations are rare)
+    if (tid < a.nr) {
+        const int ra = a.ra[tid], rb = a.rb[tid];
+        int k = 0, prev = -1;
+        const bool noop = !(rsc[tid] > 0.0);
+        for (int t = ra; t < rb; ++t) {
+            if (noop || fabs(sz[t]) <= 1e-9) { sz[t] = 0.0; continue; }
+            if (prev >= 0 && sd[t] == sd[prev]) {
+                const double r = hypot(sz[prev], sz[t]);
+                const double c = sz[t] / r, s = sz[prev] / r;
+                const int slot = atomicAdd(nrotl, 1);
+                rotl[2 * slot] = perm[prev];
+                rotl[2 * slot + 1] = perm[t];
+                rotcs[2 * slot] = (float)c;
+                rotcs[2 * slot + 1] = (float)s;
+                sz[t] = r;
+                sz[prev] = 0.0;
+            }
+            prev = t;
+        }
+        for (int t = ra; t < rb; ++t)
+            if (sz[t] != 0.0) {
+                ksd[ra + k] = sd[t];
+                ksz[ra + k] = sz[t];
+                kcol[ra + k] = perm[t];
+                ++k;
+            }
+        kcnt[tid] = k;
+    }
+    __syncthreads();
+    // ---- apply the (rare) Givens rotations to the columns, in order
+    {
+        const int nrot_ = *nrotl;
+        for (int q = 0; q < nrot_; ++q) {
+            const int cp = rotl[2 * q], ct = rotl[2 * q + 1];
+            const float c = rotcs[2 * q], s = rotcs[2 * q + 1];
+            for (int r = tid; r < d; r += MG_THREADS) {
+                const float xp = Zs[cp * ldr + r], xt = Zs[ct * ldr + r];
+                Zs[cp * ldr + r] = c * xp - s * xt;
+                Zs[ct * ldr + r] = s * xp + c * xt;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- secular roots: a pair of lanes per root (slot = tid/2 = ra + u)
+    if (myr >= 0) {
+        const int ra = a.ra[myr], u = tid - ra;
+        if (u < kcnt[myr]) kwin[tid] = ksz[ra + u] * ksz[ra + u];       // z^2 (kwin doubles as scratch)
+    }
+    __syncthreads();
+    {
+        const int slot = tid >> 1, par = tid & 1;
+        int sr = -1;
+        if (slot < d)
+            for (int r = 0; r < a.nr; ++r)
+                if (slot >= a.ra[r] && slot < a.rb[r]) sr = r;
+        const int ra = sr >= 0 ? a.ra[sr] : 0, u = slot - ra, k = sr >= 0 ? kcnt[sr] : 0;
+        const bool work = sr >= 0 && u < k;                  // uniform within the lane pair
+        const double rho = work ? rsc[sr] : 1.0;
+        const double* pd = ksd + ra;
+        const double* pz2 = kwin + ra;
+        double org = 0.0, lo = 0.0, hi = 1.0, mu = 0.5, newlam = 0.0, winv = 0.0;
+        const int kk = work ? k : 0;
+        if (work) {
+            if (u < k - 1) {
+                const double half = 0.5 * (pd[u + 1] - pd[u]);
+                org = pd[u];
+                lo = 0.0; hi = half;
+            } else {
+                double s2 = 0.0;
+                for (int i = 0; i < k; ++i) s2 += pz2[i];
+                org = pd[u]; lo = 0.0; hi = rho * s2 * 1.000001 + 1e-300;
+            }
+        }
+        // which half of the interval holds the root decides the origin (nearer pole)
+        double dl = 0.0, dr = 0.0;                 // neighbouring poles in shifted coordinates
+        const bool lastroot = work && u == k - 1;
+        {
+            const SecVal v = secular_eval<float>(pd, pz2, kk, u, org, hi, par);
+            const double fm = 1.0 + rho * (v.psi + v.phi);
+            if (work && !lastroot) {
+                const double gap = 2.0 * hi;
+                if (fm < 0.0) { org = pd[u + 1]; lo = -hi; hi = 0.0; dl = -gap; dr = 0.0; }
+                else { dl = 0.0; dr = gap; }
+            }
+        }
+        mu = 0.5 * (lo + hi);
+        // bulk of the iteration in fp32 arithmetic (differences still formed in fp64), then fp64 polish
+        bool conv = !work;
+        for (int it = 0; it < 30; ++it) {
+            if (__all_sync(0xffffffffu, conv)) break;
+            const SecVal v = secular_eval<float>(pd, pz2, kk, u, org, mu, par);
+            if (!conv) {
+                const double f = 1.0 + rho * (v.psi + v.phi);
+                const double fa = 1.0 + rho * (fabs(v.psi) + fabs(v.phi));
+                if (f > 0.0) hi = mu; else lo = mu;
+                double nx = mu + secular_step(v, rho, f, mu, dl, dr, lastroot);
+                if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
+                if (fabs(f) <= 4e-6 * fa || fabs(nx - mu) <= 2e-6 * fabs(nx) || nx == mu) conv = true;
+                mu = nx;
+            }
+        }
+        conv = !work;
+        for (int it = 0; it < 5; ++it) {
+            if (__all_sync(0xffffffffu, conv)) break;
+            const SecVal v = secular_eval<double>(pd, pz2, kk, u, org, mu, par);
+            if (!conv) {
+                const double f = 1.0 + rho * (v.psi + v.phi);
+                const double fa = 1.0 + rho * (fabs(v.psi) + fabs(v.phi));
+                if (f > 0.0) hi = mu; else lo = mu;
+                if (fabs(f) <= 2e-14 * fa) conv = true;
+                else {
+                    double nx = mu + secular_step(v, rho, f, mu, dl, dr, lastroot);
+                    if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
+                    if (fabs(nx - mu) <= 1e-13 * fabs(nx) || (hi - lo) <= 4e-16 * fmax(fabs(lo), fabs(hi))) conv = true;
+                    mu = nx;
+                }
+            }
+        }
+        // norm of the secular eigenvector (fp32 arithmetic on fp64-formed differences)
+        {
+            double n2 = 0.0;       // fp64: entries next to a pole reach 1/mu, far outside the fp32 range
+            for (int i = par; i < kk; i += 2) {
+                const double w = ksz[ra + i] * sec_rcp((pd[i] - org) - mu);
+                n2 = fma(w, w, n2);
+            }
+            n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+            winv = work ? 1.0 / sqrt(n2) : 0.0;
+            newlam = org + mu;
+        }
+        __syncthreads();               // all reads of kwin (z^2) and sd are done
+        if (work && par == 0) {
+            kmu[slot] = mu;
+            korg[slot] = org;
+            sd[slot] = winv;           // sd is dead (compact copies are used from here on)
+            lam[kcol[slot]] = (float)(rsc[4 + sr] * newlam);
+        }
+    }
+    __syncthreads();
+    // ---- W (block diagonal): Ws[ra+i][ra+t] = z_i / (d_i - lambda_t) / ||.||
+    for (int r = 0; r < a.nr; ++r) {
+        const int ra = a.ra[r], k = kcnt[r];
+        for (int idx = tid; idx < k * k; idx += MG_THREADS) {
+            const int i = idx / k, t = idx % k;
+            const double den = (ksd[ra + i] - korg[ra + t]) - kmu[ra + t];
+            Ws[(ra + i) * ldr + ra + t] = (float)(ksz[ra + i] * sec_rcp(den) * sd[ra + t]);
+        }
+    }
+    __syncthreads();
+    // ---- every column is copied first (deflated pairs keep theirs; rows outside a block are zero), then the
+    //      non-deflated ones are overwritten by Q * W (4 rows x 4 roots per thread)
+    for (int idx = tid; idx < d * d; idx += MG_THREADS) Zo[idx] = Zs[(idx / d) * ldr + (idx % d)];
+    __syncthreads();
+    for (int r = 0; r < a.nr; ++r) {
+        const int ra = a.ra[r], rb = a.rb[r], k = kcnt[r];
+        if (k == 0) continue;
+        const int row0 = ra & ~3;
+        const int nrt = (rb - row0 + 3) / 4, nct = (k + 3) / 4;
+        for (int tile = tid; tile < nrt * nct; tile += MG_THREADS) {
+            const int rt = tile % nrt, ct = tile / nrt;
+            const int r0 = row0 + 4 * rt, t0 = 4 * ct;
+            float acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+            for (int u = 0; u < k; ++u) {
+                const float4 q = *reinterpret_cast<const float4*>(Zs + (size_t)kcol[ra + u] * ldr + r0);
+                const float* wrow = Ws + (size_t)(ra + u) * ldr + ra + t0;
+                const float w0 = wrow[0], w1 = wrow[1], w2 = wrow[2], w3 = wrow[3];
+                acc[0][0] = fmaf(q.x, w0, acc[0][0]); acc[0][1] = fmaf(q.x, w1, acc[0][1]);
+                acc[0][2] = fmaf(q.x, w2, acc[0][2]); acc[0][3] = fmaf(q.x, w3, acc[0][3]);
+                acc[1][0] = fmaf(q.y, w0, acc[1][0]); acc[1][1] = fmaf(q.y, w1, acc[1][1]);
+                acc[1][2] = fmaf(q.y, w2, acc[1][2]); acc[1][3] = fmaf(q.y, w3, acc[1][3]);
+                acc[2][0] = fmaf(q.z, w0, acc[2][0]); acc[2][1] = fmaf(q.z, w1, acc[2][1]);
+                acc[2][2] = fmaf(q.z, w2, acc[2][2]); acc[2][3] = fmaf(q.z, w3, acc[2][3]);
+                acc[3][0] = fmaf(q.w, w0, acc[3][0]); acc[3][1] = fmaf(q.w, w1, acc[3][1]);
+                acc[3][2] = fmaf(q.w, w2, acc[3][2]); acc[3][3] = fmaf(q.w, w3, acc[3][3]);
+            }
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                if (t0 + y >= k) continue;
+                float* oc = Zo + (size_t)kcol[ra + t0 + y] * d;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int rr = r0 + x;
+                    if (rr >= ra && rr < rb) oc[rr] = acc[x][y];
+                }
+            }
+        }
+    }
 }
 
 // =====================================================================================
