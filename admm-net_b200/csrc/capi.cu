@@ -105,7 +105,7 @@ constexpr int NSLOT = 2;
 constexpr int TR_MAX = 88;   // largest trailing block handed to a later tridiagonalisation stage
 // orders at which the trailing block is compacted and handed to the next (smaller, higher-occupancy) stage
 inline int next_stage_order(int d) {
-    static int marks[8] = {88, 72, 56, 40, 0, 0, 0, 0};
+    static int marks[8] = {80, 64, 48, 32, 0, 0, 0, 0};
     static bool init = false;
     if (!init) {                                   // ADMMNET_STAGES="88,72,56,40" overrides the plan (tuning)
         init = true;

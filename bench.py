@@ -34,9 +34,10 @@ METRIC = "signals/s, ADMM-Net K=10 forward + peak search"
 FLOP_PER_LAYER = 33.1e6          # eigh 24 d^3 + rebuild 8 d^3 + 0.15 MFLOP elementwise
 FLOP_PEAK_SEARCH = 0.86e6        # separable coarse surface
 BYTES_PER_SIGNAL = 2404          # y 800 + b 800 + sigma 4 in, phi 800 out
-# implementation DRAM traffic of the four layer kernels per signal-layer, from the ncu --set full capture in
-# profiles/r01_ncu_summary.md (dram__bytes_read+write over 4096 signals): 157 + 53 + 98 + 114 KB
-TRAFFIC_PER_SIGNAL_LAYER = 421.8e3
+# implementation DRAM traffic of the layer kernels per signal-layer, from the ncu --set full capture in
+# profiles/r01_ncu_summary.md (dram__bytes_read+write over 4096 signals): k_head 180 + k_head2 (4 stages) 174 +
+# k_ql 56 + k_rot 102 + k_tail 114 KB
+TRAFFIC_PER_SIGNAL_LAYER = 626e3
 
 
 def tile_signals(B, seed):
@@ -274,13 +275,16 @@ def main():
     gpu_ms = sum(v["ms_per_step"] for v in kern.values())
     for v in kern.values():
         v["share"] = v["ms_per_step"] / gpu_ms
-    eig = ("k_head", "k_ql", "k_rot", "k_tail")
-    eig_ms = sum(kern[k]["ms_per_step"] for k in eig if k in kern)
+    eig = ("k_head", "k_head2", "k_ql", "k_rot", "k_merge", "k_tail")
     eig_launch = sum(kern[k]["launches_per_step"] for k in eig if k in kern)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
-    achieved = FLOP_PER_LAYER * (K_LAYERS - 1) * B / (eig_ms * 1e-3) / 1e12
+    # device time of the K-layer forward: the step minus the peak-search launch (which runs alone, after the
+    # forward, on the same stream).  The per-kernel event sums of the layer kernels overlap across the chunk
+    # lanes, so they give shares, not the forward's duration.
+    fwd_ms = ms_step - kern.get("k_peak_search", {"ms_per_step": 0.0})["ms_per_step"]
+    achieved = FLOP_PER_LAYER * (K_LAYERS - 1) * B / (fwd_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,14 +301,15 @@ def main():
                 "d2h_bytes_per_step": int(phi_h.nbytes + top_h.nbytes + cnt_h.nbytes)},
         "gpu_launches": int(sum(kln[i] for i in range(nk))),
         "roofline": {
-            "bound": "fp32", "kernel": "layer pipeline k_head+k_ql+k_rot+k_tail (dominant: %s)" % dom,
+            "bound": "fp32", "kernel": "layer pipeline k_head+k_head2+k_ql+k_rot+k_tail (dominant: %s)" % dom,
+            "forward_ms_per_step": fwd_ms,
             "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
             "traffic": TRAFFIC_PER_SIGNAL_LAYER * (K_LAYERS - 1) * B,
             "traffic_note": "bytes per step of the four layer kernels (profiles/r01_ncu_summary.md); algorithmic "
                             "bytes per step are 2404 B x signals: the path is compute bound, the extra traffic is "
                             "per-layer state (packed Z, G, reflectors, rotation stream) at <5 % of HBM bandwidth",
             "note": "FP32-FMA/shared-memory bound eigen-solver (SURVEY.md §8d): algorithmic 33.1 MFLOP per signal-layer x "
-                    "(K-1) layers / summed CUDA-event time of the four kernels; peak = FP32 FFMA micro-kernel measured "
+                    "(K-1) layers / device time of the forward (step minus the peak-search launch); peak = FP32 FFMA micro-kernel measured "
                     "live (MEASURED_PEAKS.json has no FP32 figure). launches per step: %d" % eig_launch,
             "hbm": {"achieved_gbs": BYTES_PER_SIGNAL * B / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "peak_source": "measured" if peaks else "fallback"},
