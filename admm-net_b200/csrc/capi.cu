@@ -170,15 +170,17 @@ int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
 // QL).  Measured on B200 (131072 signals x 9 layers): L=3 cuts k_ql 292 -> 85 ms and k_rot 468 -> 157 ms per step, but
 // the fp64-flavoured secular solves of k_merge cost 1690 ms, so the path is validated (all parity tests pass with
 // ADMMNET_DC=1..3) but off by default until the merge is rewritten in fp32 with Loewner-corrected z.
-inline int dc_levels(int d) {
-    static const int env = getenv("ADMMNET_DC") ? atoi(getenv("ADMMNET_DC")) : 0;
-    int L = env < 0 ? 0 : (env > 3 ? 3 : env);
+// Small batches are the exception: there the single-thread QL chain (8.5k dependent rotations, ~1.7 ms per layer) is
+// pure latency, D&C shortens it 7x and the merges are cheap in absolute terms, so B <= 1024 defaults to L = 3.
+inline int dc_levels(int d, int B) {
+    static const int env = getenv("ADMMNET_DC") ? atoi(getenv("ADMMNET_DC")) : -1;
+    int L = env < 0 ? (B <= 1024 ? 3 : 0) : (env > 3 ? 3 : env);
     while (L > 0 && (d >> L) < 8) --L;        // blocks of at least 8
     return L;
 }
-inline TearSpec dc_tears(int d) {
+inline TearSpec dc_tears(int d, int B) {
     TearSpec ts;
-    const int L = dc_levels(d), nb = 1 << L;
+    const int L = dc_levels(d, B), nb = 1 << L;
     ts.n = nb - 1;
     for (int q = 0; q < ts.n; ++q) ts.pos[q] = (int)(((long long)(q + 1) * d) / nb);
     return ts;
@@ -229,7 +231,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
-                                                                         status, dc_tears(d), w.rho);
+                                                                         status, dc_tears(d, B), w.rho);
         CK(cudaGetLastError());
     }
     if (side) {
@@ -246,8 +248,8 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
     // divide & conquer merges, leaves -> root; Z ping-pongs between the two scratch buffers
     const float* zfinal = w.Zr;
     {
-        const TearSpec ts = dc_tears(d);
-        const int L = dc_levels(d);
+        const TearSpec ts = dc_tears(d, B);
+        const int L = dc_levels(d, B);
         float* zb[2] = {w.Zr, w.Zr2};
         int cur = 0;
         for (int lev = 1; lev <= L; ++lev) {

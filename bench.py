@@ -146,6 +146,63 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _time_ms(fn, reps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_extras(pkg, dev):
+    """The other BASELINE.json configs, measured on rank 0 after the headline run (not bench lines of their own):
+    configs[0] single-signal latency (what results/time/*.txt of the reference publish), configs[1] classical ADMM
+    at batch 64k against the HBM roofline, configs[3] peak-search dictionary sweep."""
+    from oracle import signals
+    out = {}
+    # configs[0]: B = 1, K = 10 / 5, host tensors in and out (test/test_time_net.py:98-100 times model(y,b,sigma))
+    y, b, s, _ = signals.generate(1, seed=5)
+    yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
+    for K in (10, 5):
+        torch.manual_seed(0)
+        net = pkg.PhiEstADMMNet(M, N, 3, K).eval()
+        net(yt, bt, st)
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            net(yt, bt, st)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out[f"latency_b1_k{K}_ms"] = float(np.median(ts))
+    out["latency_published_ms"] = {"k10_mean": 191.0, "k5_mean": 96.5, "classic_mean": 524.4,
+                                   "source": "results/time/time_net.txt, time_net_5.txt, time.txt (hardware not stated)"}
+    # configs[1]: classical ADMM, batch 65536, complex64 inputs -> complex128 phi, 5 iterations (what admm_for_us executes)
+    Bc = 65536
+    y, b, s = tile_signals(Bc, seed=77)
+    yd, bd = torch.from_numpy(y).to(dev), torch.from_numpy(b).to(dev)
+    o = torch.empty(Bc, M * N, dtype=torch.complex128, device=dev)
+    pkg.admm_for_us_batched(yd, bd, 1.0, 5, out=o)
+    ms = _time_ms(lambda: pkg.admm_for_us_batched(yd, bd, 1.0, 5, out=o), 20)
+    byt = Bc * (800 + 800 + 1600)
+    out["classic_64k"] = {"signals_per_s": Bc / (ms * 1e-3), "ms": ms, "algorithmic_bytes": byt,
+                          "achieved_gbs": byt / (ms * 1e-3) / 1e9,
+                          "note": "c64 y,b in / c128 phi out = 3204 B per signal; working set 210 MB > 126 MB L2"}
+    # configs[3]: peak-search steering-dictionary sweep (SURVEY.md §0: n x grid), batch 8192 per point
+    sweep = []
+    rng = np.random.default_rng(3)
+    for nb, g in ((8, 32), (10, 45), (12, 64), (16, 64)):
+        Bp = 8192
+        phi = torch.from_numpy((rng.normal(size=(Bp, nb * nb)) + 1j * rng.normal(size=(Bp, nb * nb))).astype(np.complex64)).to(dev)
+        opts = dict(xstep=1.0 / g, ystep=1.0 / g, iter=3)
+        pkg.alt_peak_search_batched(phi, nb, nb, opts, topl=3, pmax=512)
+        ms = _time_ms(lambda: pkg.alt_peak_search_batched(phi, nb, nb, opts, topl=3, pmax=512), 3)
+        sweep.append({"n": nb * nb, "grid": f"{g - 1}x{g - 1}", "signals_per_s": Bp / (ms * 1e-3)})
+    out["peak_search_sweep"] = sweep
+    return out
+
+
 def workload_config(args):
     return {"workload": f"BASELINE.json configs[2]: ADMM-Net K={K_LAYERS}, n={M}x{N}, forward + alt_peak_search "
                         f"(99x99, iter=3, top-{TOPL}); {args.per_gpu} signals per GPU per step (1M/8), weak scaling",
@@ -163,6 +220,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--norm-scope", default="shard", choices=["shard", "global"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -270,6 +328,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    extras = None if args.no_extras else measure_extras(admmnet_b200, dev)
     names = [L.admmnet_profile_kind_name(i).decode() for i in range(nk)]
     kern = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kln[i] / args.steps} for i in range(nk) if kln[i]}
     gpu_ms = sum(v["ms_per_step"] for v in kern.values())
@@ -315,6 +374,8 @@ def main():
                     "peak_source": "measured" if peaks else "fallback"},
             "kernels": kern},
     }
+    if extras is not None:
+        line["extras"] = extras
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, tf, tp = cpu_sample(192, 4, cores)
