@@ -156,6 +156,27 @@ def test_forward_vs_oracle_seeded_batch_and_scopes(pkg):
     assert rel_err(ref_c.numpy(), ref.numpy()).max() > PHI_TOL      # the coupling is material
 
 
+def test_ql_and_divide_and_conquer_paths_agree(pkg):
+    """Launches of more than 1024 signals use plain QL for the tridiagonal eigenproblem, smaller ones the
+    divide & conquer merge kernel (capi.cu::dc_levels).  Same batch, same whole-batch norm scope, two scratch
+    chunk sizes -> both paths; they must agree with each other and with the oracle."""
+    from oracle import net_oracle, signals
+    torch.manual_seed(11)
+    net = pkg.PhiEstADMMNet(10, 10, 3, 6).eval()
+    y, b, s, _ = signals.generate(1280, seed=29)
+    yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
+    net.chunk = 4096                                   # one launch of 1280 signals: QL path
+    with torch.no_grad():
+        phi_ql = net(yt, bt, st).numpy()
+    net.chunk = 320                                    # four launches of 320 signals: D&C path
+    with torch.no_grad():
+        phi_dc = net(yt, bt, st).numpy()
+    assert rel_err(phi_dc, phi_ql).max() < 3e-5
+    ref = net_oracle.forward(net.state_dict(), yt, bt, st, 10, 10, 6).numpy()
+    assert rel_err(phi_ql, ref).max() < PHI_TOL
+    assert rel_err(phi_dc, ref).max() < PHI_TOL
+
+
 def test_forward_other_shapes_and_edges(pkg):
     from oracle import net_oracle, signals
     torch.manual_seed(5)
