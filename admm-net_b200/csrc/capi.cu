@@ -567,14 +567,14 @@ extern "C" int admm_classic_forward(const void* y, const void* b, int in_is_c128
     if (!y || !b || !phi_out) return fail(ADMMNET_ERR_ARG, "null pointer");
     if (B <= 0 || n <= 0 || n > 256 || n_iter < 0) return fail(ADMMNET_ERR_ARG, "need B > 0, 0 < n <= 256, n_iter >= 0");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (int)(((long long)B * 32 + 255) / 256);
     prof::Scope pscope(prof::CLASSIC, st);
+    const int grid = (int)(((long long)B * 32 + 255) / 256);      // one warp per signal
     if (n <= 128) {
-        if (in_is_c128) k_classic<double2, 4><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
-        else k_classic<float2, 4><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        if (in_is_c128) k_classic<double2, 4, 32><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        else k_classic<float2, 4, 32><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
     } else {
-        if (in_is_c128) k_classic<double2, 8><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
-        else k_classic<float2, 8><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        if (in_is_c128) k_classic<double2, 8, 32><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        else k_classic<float2, 8, 32><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
     }
     CK(cudaGetLastError());
     return 0;
