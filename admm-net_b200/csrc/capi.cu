@@ -9,6 +9,7 @@
 #include "net_kernels.cu"
 #include "classic_kernels.cu"
 #include "peak_kernels.cu"
+#include "gen_kernels.cu"
 
 using namespace admmnet;
 
@@ -645,5 +646,21 @@ extern "C" int admmnet_fp32_peak_launch(float* out, int grid, int iters, double*
     k_fma_peak<<<grid, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
     CK(cudaGetLastError());
     if (flops) *flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ synthetic inputs
+extern "C" int admmnet_generate(void* y, void* b, float* sigma, double* truth, int B, int Nb, int Nd, int L,
+                                double snr_w_db, double snr_demod_db, unsigned long long seed, void* stream) {
+    if (!y || !b || !sigma) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (B <= 0 || Nb < 1 || Nd < 1 || Nb * Nd > 256 || L < 1 || L > GEN_MAXL)
+        return fail(ADMMNET_ERR_ARG, "need B > 0, Nb*Nd <= 256, 1 <= L <= 8");
+    GenArgs a;
+    a.y = (float2*)y; a.b = (float2*)b; a.sigma = sigma; a.truth = truth;
+    a.B = B; a.Nb = Nb; a.Nd = Nd; a.L = L; a.snr_w_db = snr_w_db; a.snr_demod_db = snr_demod_db; a.seed = seed;
+    const long long nthreads = (long long)B * 32;
+    prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
+    k_generate<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
     return 0;
 }

@@ -244,9 +244,9 @@ def main():
     model = admmnet_b200.PhiEstADMMNet(M, N, 3, K_LAYERS).eval()
     model.chunk = args.chunk
     model.check_status = False               # status word is read once after the timed region
-    y, b, s = tile_signals(B, seed=1234 + rank)
-    yh, bh, sh = (torch.from_numpy(a).pin_memory() for a in (y, b, s))
-    yd, bd, sd_ = yh.to(dev), bh.to(dev), sh.to(dev)
+    # B unique signals of the generate_data.py recipe, generated on the device (csrc/gen_kernels.cu), seed = 1234 + rank
+    yd, bd, sd_ = admmnet_b200.generate_signals(B, M, N, 3, snr_w=20.0, snr_demod=7.0, seed=1234 + rank, device=dev)
+    yh, bh, sh = (t.cpu().pin_memory() for t in (yd, bd, sd_))
     phi_h = torch.empty(B, M * N, dtype=torch.complex64).pin_memory()
     top_h = torch.empty(B, TOPL, 3, dtype=torch.float64).pin_memory()
     cnt_h = torch.empty(B, dtype=torch.int32).pin_memory()

@@ -119,6 +119,14 @@ int peak_search_points(const void* phi, int phi_is_c128, int xbase, int ybase, c
                        int npts, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Synthetic inputs on the device (replaces the per-sample Python loop of generate_data.py:133-221 as the input
+ * generator of benchmarks; counter-based RNG keyed by (seed, signal index))
+ *   y, b   complex64 [B][Nb*Nd], sigma float32 [B]; truth optional float64 [B][L][4] = (tau, f, Re C, Im C)
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_generate(void* y, void* b, float* sigma, double* truth, int B, int Nb, int Nd, int L, double snr_w_db,
+                     double snr_demod_db, unsigned long long seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): per-kernel CUDA-event timing of the launches issued between
  * admmnet_profile_begin and admmnet_profile_end (summed ms and launch count per kernel kind), and an
  * FP32-FMA peak micro-kernel (roofline denominator of the FP32-pipe-bound eigen-solver kernels).

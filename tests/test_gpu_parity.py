@@ -301,3 +301,45 @@ def test_end_to_end_recovers_targets(pkg):
         amp = np.abs(truth["C"][i])
         j = int(np.argmax(amp))
         assert abs(top[0][0] - truth["tau"][i][j]) < 0.05 and abs(top[0][1] - truth["f"][i][j]) < 0.05
+
+
+def test_device_signal_generator(pkg):
+    """admmnet_generate follows generate_data.py:133-221: structural identities + statistics + determinism."""
+    B, Nb, Nd, L = 4096, 10, 10, 3
+    y, b, s, truth = pkg.generate_signals(B, Nb, Nd, L, snr_w=20.0, snr_demod=7.0, seed=99, return_truth=True)
+    y2, b2, s2 = pkg.generate_signals(64, Nb, Nd, L, snr_w=20.0, snr_demod=7.0, seed=99)
+    assert torch.equal(y[:64], y2) and torch.equal(b[:64], b2) and torch.equal(s[:64], s2)     # counter-based RNG
+    y3, _, _ = pkg.generate_signals(64, Nb, Nd, L, seed=100)
+    assert not torch.equal(y3, y2)
+    y, b, s, truth = y.cpu().numpy(), b.cpu().numpy(), s.cpu().numpy().astype(np.float64), truth.cpu().numpy()
+    # b on the QPSK constellation with phase offset pi/4 (generate_data.py:210-218)
+    np.testing.assert_allclose(np.abs(b), 1.0, atol=1e-6)
+    k = (np.angle(b) - np.pi / 4) / (np.pi / 2)
+    np.testing.assert_allclose(k, np.round(k), atol=1e-5)
+    # sigma = ||e/b|| + 1 with |e|^2 in {0, 2, 4} per symbol; symbol error rate of QPSK at 7 dB is a few per cent
+    q = (s - 1.0) ** 2 / 2.0
+    np.testing.assert_allclose(q, np.round(q), atol=1e-3)
+    assert 0.5 < q.mean() < 8.0
+    # parameter ranges (generate_data.py:30-31, 142-144)
+    tau, f, C = truth[..., 0], truth[..., 1], truth[..., 2] + 1j * truth[..., 3]
+    assert tau.min() >= 0.1 and tau.max() <= 0.9 and f.min() >= -0.4 and f.max() <= 0.4
+    assert abs(C.real.std() - 0.7) < 0.03 and abs(C.imag.std() - 0.7) < 0.03 and abs(C.mean()) < 0.05
+    # y = (b+e) Psi + w: on error-free symbols the residual y - b Psi is the noise w at SNR 20 dB
+    p_idx, q_idx = np.divmod(np.arange(Nb * Nd), Nd)
+    Psi = np.einsum("bl,blp,blq->bpq", C, np.exp(2j * np.pi * f[..., None] * np.arange(Nb)),
+                    np.exp(-2j * np.pi * tau[..., None] * np.arange(Nd))).reshape(B, -1)
+    res = np.abs(y - b * Psi) ** 2
+    sig_pow = (np.abs(Psi) ** 2).mean(axis=1)
+    ratio = np.median(res, axis=1) / sig_pow                      # median ignores the few symbol errors
+    # median of an exponential = ln2 * mean ; mean noise power = signal power / 100
+    assert abs(np.mean(ratio) / (np.log(2) * 0.01) - 1.0) < 0.1
+    # end to end: the strongest target is recovered from generated data by the classical path
+    yq, bq, sq, tq = pkg.generate_signals(4, Nb, Nd, L, snr_demod=30.0, seed=5, return_truth=True)
+    for i in range(4):
+        phi, _ = pkg.admm_for_us(yq[i].cpu().numpy().astype(np.complex128), bq[i].cpu().numpy().astype(np.complex128),
+                                 10, 10, 1.0, float(sq[i]))
+        pk = pkg.alt_peak_search({"phi": phi, "xbase": 10, "ybase": 10}, dict(xstep=0.01, ystep=0.01, iter=3))
+        top = max(pk, key=lambda r: r[2])
+        t = tq[i].cpu().numpy()
+        j = int(np.argmax(np.hypot(t[:, 2], t[:, 3])))
+        assert abs(top[0] - t[j, 0]) < 0.05 and abs(top[1] - t[j, 1]) < 0.05
