@@ -12,7 +12,7 @@ Differences from the reference, all documented in DESIGN.md:
   * `norm_scope` / `chunk` attributes control how the ZLayer batch mean (admm_net.py:459) is scoped:
       'batch' (default) = the whole batch of the call, exactly like the reference;
       'chunk'           = independent chunks of `chunk` signals (throughput mode, no coupling);
-  * `ADMMNet`'s learned PeakSearchLayer head (admm_net.py:494-720) is not part of this round's hot path.
+  * `ADMMNet`'s learned PeakSearchLayer head (admm_net.py:494-630) runs with eval-mode semantics.
 """
 import ctypes as C
 import warnings
@@ -197,11 +197,73 @@ class PhiEstADMMNet(nn.Module):
         return out if src_dev.type == "cuda" else out.to(src_dev)
 
 
+class PeakSearchLayer(nn.Module):
+    """Parameter holder for the learned regression head (admm_net.py:494-554): same sub-module names, shapes and
+    construction order as the reference, so `state_dict`s are interchangeable and a seeded init matches."""
+
+    def __init__(self, M, N, L=3, hidden_dim=128, num_heads=4):
+        super().__init__()
+        if hidden_dim != 128 or num_heads != 4:
+            raise ValueError("the B200 head kernel is built for hidden_dim=128, num_heads=4 (the reference's defaults)")
+        self.M, self.N, self.L_max = M, N, L
+        self.dim = M * N
+        self.feature_extractor = nn.Sequential(nn.Linear(2 * self.dim, hidden_dim), nn.ReLU(),
+                                               nn.Linear(hidden_dim, hidden_dim), nn.ReLU())
+        tau_grid, f_grid = torch.meshgrid(torch.linspace(0, 1, M), torch.linspace(-0.5, 0.5, N), indexing="ij")
+        self.position_encoder = nn.Parameter(torch.stack([tau_grid.flatten(), f_grid.flatten()], dim=1),
+                                             requires_grad=True)                       # admm_net.py:556-568
+        self.position_projection = nn.Linear(2, hidden_dim)
+        self.attention = nn.MultiheadAttention(embed_dim=hidden_dim, num_heads=num_heads, batch_first=True, dropout=0.1)
+        self.peak_extractor = nn.Sequential(nn.Linear(hidden_dim, hidden_dim // 2), nn.ReLU(),
+                                            nn.Linear(hidden_dim // 2, hidden_dim // 4), nn.ReLU(),
+                                            nn.Linear(hidden_dim // 4, hidden_dim // 8), nn.ReLU())
+        self.tau_regressor = nn.ModuleList([nn.Sequential(nn.Linear(hidden_dim // 8, 32), nn.ReLU(), nn.Linear(32, 1),
+                                                          nn.Sigmoid()) for _ in range(L)])
+        self.f_regressor = nn.ModuleList([nn.Sequential(nn.Linear(hidden_dim // 8, 32), nn.ReLU(), nn.Linear(32, 1),
+                                                        nn.Tanh()) for _ in range(L)])
+        self.confidence_net = nn.Sequential(nn.Linear(hidden_dim // 8, 16), nn.ReLU(), nn.Linear(16, 1), nn.Sigmoid())
+
+
 class ADMMNet(PhiEstADMMNet):
-    """admm_net.py:767-816 minus the learned PeakSearchLayer head (not built yet):
-    the unrolled loop is shared with PhiEstADMMNet; use utils.peakSearchUtils.alt_peak_search on phi."""
+    """admm_net.py:767-816.  forward(y, b, sigma) -> (tau_est, f_est, confidences, phi): the unrolled loop is shared
+    with PhiEstADMMNet; the PeakSearchLayer head (admm_net.py:570-630) runs in csrc/head_kernels.cu with eval-mode
+    semantics (no attention dropout)."""
+
+    def __init__(self, M, N, L=3, num_layers=10):
+        super().__init__(M, N, L, num_layers)
+        self.peakSearchLayer = PeakSearchLayer(M, N, L)
+        self._head = None
+        self._head_key = None
+
+    def packed_head(self, device):
+        from .params import pack_head
+        ps = list(self.peakSearchLayer.parameters())
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in ps)
+        if self._head is None or self._head_key != key:
+            self._head = pack_head(self.state_dict(), self.M * self.N, self.L).to(device)
+            self._head_key = key
+        return self._head
+
+    def head_device(self, phi):
+        """phi complex64 [B,n] on the GPU -> (tau, f, conf) float32 [B,L] on the GPU."""
+        B, n, L = phi.shape[0], self.M * self.N, self.L
+        dev = phi.device
+        H = self.packed_head(dev)
+        tau, f, conf = (torch.empty(B, L, dtype=torch.float32, device=dev) for _ in range(3))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(_capi.lib().admmnet_peak_head(phi.contiguous().data_ptr(), B, n, L, H.data_ptr(), tau.data_ptr(),
+                                                  f.data_ptr(), conf.data_ptr(), stream))
+        return tau, f, conf
 
     def forward(self, y, b, sigma):
-        raise NotImplementedError(
-            "ADMMNet's learned PeakSearchLayer head (admm_net.py:494-720) is outside this round's hot path; "
-            "use PhiEstADMMNet + alt_peak_search (main_for_net.py:99-117)")
+        if self.training and not self._warned:
+            warnings.warn("admmnet_b200: ADMMNet runs its head with eval-mode semantics (no attention dropout)")
+        src_dev = y.device
+        yd, bd, sd, _ = self._prep(y, b, sigma)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned:
+            warnings.warn("admmnet_b200: forward is an inference fast path; the result is detached from autograd")
+            self._warned = True
+        phi = self.forward_device(yd, bd, sd)
+        tau, f, conf = self.head_device(phi)
+        outs = (tau, f, conf, phi)
+        return outs if src_dev.type == "cuda" else tuple(t.to(src_dev) for t in outs)

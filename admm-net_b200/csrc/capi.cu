@@ -10,6 +10,7 @@
 #include "classic_kernels.cu"
 #include "peak_kernels.cu"
 #include "gen_kernels.cu"
+#include "head_kernels.cu"
 
 using namespace admmnet;
 
@@ -661,6 +662,22 @@ extern "C" int admmnet_generate(void* y, void* b, float* sigma, double* truth, i
     const long long nthreads = (long long)B * 32;
     prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
     k_generate<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ ADMMNet regression head
+extern "C" int admmnet_head_param_count(int n, int L) { return head_param_count(n, L); }
+extern "C" int admmnet_peak_head(const void* phi, int B, int n, int L, const float* head_params, float* tau, float* f,
+                                 float* conf, void* stream) {
+    if (!phi || !head_params || !tau || !f || !conf) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (B <= 0 || n < 1 || n > 128 || L < 1 || L > 8) return fail(ADMMNET_ERR_ARG, "need B > 0, n <= 128, 1 <= L <= 8");
+    HeadArgs2 a;
+    a.phi = (const float2*)phi; a.P = head_params; a.tau = tau; a.f = f; a.conf = conf; a.B = B; a.n = n; a.L = L;
+    const size_t sm = (size_t)(HS * 2 * n + 3 * HS * HD + HS * HEADS * n) * sizeof(float);
+    CK(cudaFuncSetAttribute(k_peak_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
+    k_peak_head<<<(B + HS - 1) / HS, HD, sm, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return 0;
 }

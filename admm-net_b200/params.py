@@ -53,3 +53,44 @@ def pack_state_dict(sd, n, num_layers):
         r[P_HW1T + 64 * n:P_HW1T + 128 * n] = W2.t().contiguous().reshape(-1)     # [64][n]
         r[P_HW1T + 128 * n:P_HW1T + 129 * n] = g(f"hLayers.{k}.correction_net.2.bias")
     return out
+
+
+HD = 128
+
+
+def head_param_count(n, L):
+    base = (2 * n * HD + HD) + 3 * (HD * HD + HD) + 2 * n * HD + (HD * 64 + 64) + (64 * 32 + 32) + (32 * 16 + 16)
+    return base + L * 2 * (16 * 32 + 32 + 32 + 1) + (16 * 16 + 16 + 16 + 1)
+
+
+@torch.no_grad()
+def pack_head(sd, n, L, prefix="peakSearchLayer."):
+    """Pack PeakSearchLayer's parameters (admm_net.py:496-554) for csrc/head_kernels.cu.  Weights are stored
+    transposed ([in][out]); the attention keys/values only depend on the parameters (key = value =
+    position_projection(position_encoder), admm_net.py:595-603), so K and V are projected here once with the same
+    fp32 torch ops nn.MultiheadAttention applies."""
+    g = lambda name: sd[prefix + name].detach().to("cpu", torch.float32)
+    parts = []
+    T = lambda w: w.t().contiguous().reshape(-1)
+    parts += [T(g("feature_extractor.0.weight")), g("feature_extractor.0.bias")]
+    parts += [T(g("feature_extractor.2.weight")), g("feature_extractor.2.bias")]
+    Wi, bi = g("attention.in_proj_weight"), g("attention.in_proj_bias")
+    Wq, Wk, Wv = Wi[:HD], Wi[HD:2 * HD], Wi[2 * HD:]
+    bq, bk, bv = bi[:HD], bi[HD:2 * HD], bi[2 * HD:]
+    parts += [T(Wq), bq]
+    pos = F.linear(g("position_encoder"), g("position_projection.weight"), g("position_projection.bias"))   # [n, HD]
+    K = F.linear(pos, Wk, bk)                                      # [n, HD]
+    V = F.linear(pos, Wv, bv)
+    parts += [K.t().contiguous().reshape(-1), V.contiguous().reshape(-1)]
+    parts += [T(g("attention.out_proj.weight")), g("attention.out_proj.bias")]
+    for i in (0, 2, 4):
+        parts += [T(g(f"peak_extractor.{i}.weight")), g(f"peak_extractor.{i}.bias")]
+    for t in range(L):
+        for kind in ("tau_regressor", "f_regressor"):
+            parts += [T(g(f"{kind}.{t}.0.weight")), g(f"{kind}.{t}.0.bias"), g(f"{kind}.{t}.2.weight").reshape(-1),
+                      g(f"{kind}.{t}.2.bias").reshape(-1)]
+    parts += [T(g("confidence_net.0.weight")), g("confidence_net.0.bias"), g("confidence_net.2.weight").reshape(-1),
+              g("confidence_net.2.bias").reshape(-1)]
+    out = torch.cat([p.reshape(-1) for p in parts])
+    assert out.numel() == head_param_count(n, L), (out.numel(), head_param_count(n, L))
+    return out

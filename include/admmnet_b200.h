@@ -119,6 +119,16 @@ int peak_search_points(const void* phi, int phi_is_c128, int xbase, int ybase, c
                        int npts, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ADMMNet's learned regression head  (replaces PeakSearchLayer.forward, admm_net.py:570-630, eval mode)
+ *   phi           complex64 [B][n], n = M*N <= 128
+ *   head_params   float32 [admmnet_head_param_count(n, L)], packed by admm-net_b200/params.py::pack_head
+ *   tau, f, conf  float32 [B][L]
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_head_param_count(int n, int L);
+int admmnet_peak_head(const void* phi, int B, int n, int L, const float* head_params, float* tau, float* f,
+                      float* conf, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Synthetic inputs on the device (replaces the per-sample Python loop of generate_data.py:133-221 as the input
  * generator of benchmarks; counter-based RNG keyed by (seed, signal index))
  *   y, b   complex64 [B][Nb*Nd], sigma float32 [B]; truth optional float64 [B][L][4] = (tau, f, Re C, Im C)

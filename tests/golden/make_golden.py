@@ -43,11 +43,19 @@ def import_reference():
     sys.modules["skimage"] = sk
     sys.modules["skimage.morphology"] = skm
     sys.modules["cvxpy"] = types.ModuleType("cvxpy")
+    # the repository ships drop-in modules with the reference's names (admm_net, admm, utils.*): make sure the
+    # REFERENCE's files are the ones imported here.  `utils` needs care: ours is a regular package and would
+    # shadow the reference's namespace package whatever the sys.path order.
+    upkg = types.ModuleType("utils")
+    upkg.__path__ = [os.path.join(REF, "utils")]
+    sys.modules["utils"] = upkg
     import admm_net  # noqa
     import admm  # noqa
     import utils.peakSearchUtils as psu  # noqa
     import utils.mathUtils as mu  # noqa
     admm.admm_for_us_H_cvx_0 = classic_oracle.h_update
+    for m in (admm_net, admm, psu, mu):
+        assert os.path.abspath(m.__file__).startswith(REF), m.__file__
     return admm_net, admm, psu, mu
 
 
@@ -142,6 +150,18 @@ def main():
         print(tag, "phi max", np.abs(phi).max())
         if tag == "init_k10":
             phi_for_peaks = phi
+
+    # ------------------------------------------------------------------ full ADMMNet (unrolled loop + PeakSearchLayer head)
+    torch.manual_seed(3)
+    full = admm_net.ADMMNet(10, 10, 3, 3).eval()
+    perturb_(full, 9)
+    with torch.no_grad():
+        tau_e, f_e, conf_e, phi_e = full(ty, tb, ts)
+        tau_h, f_h, conf_h = full.peakSearchLayer(phi_e)          # head alone on the reference's own phi
+    np.savez(os.path.join(HERE, "admmnet_full_k3.npz"), y=y_all, b=b_all, sigma=s_all, K=3, M=10, N=10, L=3,
+             tau=tau_e.numpy(), f=f_e.numpy(), conf=conf_e.numpy(), phi=phi_e.numpy(),
+             **{"sd__" + k: v for k, v in sd_to_npz(full.state_dict()).items()})
+    print("ADMMNet tau", tau_e[0].numpy(), "f", f_e[0].numpy(), "conf", conf_e[0].numpy())
 
     # ------------------------------------------------------------------ classical ADMM
     import contextlib

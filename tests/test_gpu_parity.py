@@ -343,3 +343,27 @@ def test_device_signal_generator(pkg):
         t = tq[i].cpu().numpy()
         j = int(np.argmax(np.hypot(t[:, 2], t[:, 3])))
         assert abs(top[0] - t[j, 0]) < 0.05 and abs(top[1] - t[j, 1]) < 0.05
+
+
+def test_admmnet_full_module_matches_reference_golden(pkg):
+    """ADMMNet.forward (admm_net.py:791-816): unrolled loop + PeakSearchLayer head, against the reference's outputs."""
+    z = np.load(os.path.join(GOLDEN, "admmnet_full_k3.npz"))
+    sd = {k[4:].replace("__", "."): torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}
+    net = pkg.ADMMNet(10, 10, 3, 3).eval()
+    net.load_state_dict(sd)
+    y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
+    with torch.no_grad():
+        tau, f, conf, phi = net(y, b, s)
+    assert tau.shape == (7, 3) and f.shape == (7, 3) and conf.shape == (7, 3) and phi.shape == (7, 100)
+    assert rel_err(phi.numpy(), z["phi"]).max() < PHI_TOL
+    np.testing.assert_allclose(tau.numpy(), z["tau"], atol=2e-4)
+    np.testing.assert_allclose(f.numpy(), z["f"], atol=2e-4)
+    np.testing.assert_allclose(conf.numpy(), z["conf"], atol=2e-4)
+    # the head alone on the reference's own phi: plain fp32 MLP/attention arithmetic
+    t2, f2, c2 = net.head_device(torch.from_numpy(z["phi"]).cuda())
+    np.testing.assert_allclose(t2.cpu().numpy(), z["tau"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(f2.cpu().numpy(), z["f"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(c2.cpu().numpy(), z["conf"], atol=2e-6, rtol=1e-5)
+    # ragged batch (not a multiple of the 8 signals a CTA takes)
+    t3, _, _ = net.head_device(torch.from_numpy(z["phi"][:5]).cuda())
+    np.testing.assert_allclose(t3.cpu().numpy(), z["tau"][:5], atol=2e-6, rtol=1e-5)

@@ -86,6 +86,26 @@ def test_module_mirror_state_dict_and_seeded_init(built):
     assert len(groups) == len(list(net.parameters()))                # trainPhi.py:106-111 grouping still matches
 
 
+def test_admmnet_mirror_accepts_reference_state_dict(built):
+    import admm_net
+    from admmnet_b200 import params
+    z = np.load(os.path.join(ROOT, "tests", "golden", "admmnet_full_k3.npz"))
+    sd = {k[4:].replace("__", "."): torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}
+    net = admm_net.ADMMNet(10, 10, 3, 3)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd)
+    H = params.pack_head(net.state_dict(), 100, 3)
+    assert H.numel() == built.lib().admmnet_head_param_count(100, 3) == params.head_param_count(100, 3)
+    W1 = sd["peakSearchLayer.feature_extractor.0.weight"]
+    assert torch.equal(H[:200 * 128].reshape(200, 128), W1.t())
+    # seeded construction consumes the RNG exactly like the reference (same module order)
+    torch.manual_seed(0)
+    a = admm_net.ADMMNet(4, 5, 2, 2)
+    assert a.peakSearchLayer.position_encoder.shape == (20, 2)
+    assert float(a.peakSearchLayer.position_encoder[5, 0]) == pytest.approx(1 / 3) and \
+        float(a.peakSearchLayer.position_encoder[5, 1]) == pytest.approx(-0.5)
+
+
 def test_product_path_has_no_cpu_fallback(built):
     import admm_net
     import admm
