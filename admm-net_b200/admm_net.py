@@ -8,7 +8,8 @@ The layer modules only HOLD parameters; the arithmetic of `PhiEstADMMNet.forward
 kernels behind include/admmnet_b200.h (no PyTorch/CPU fallback).
 
 Differences from the reference, all documented in DESIGN.md:
-  * forward is an inference fast path: the result carries no autograd graph;
+  * eval-mode forward is an inference fast path (no autograd graph); in train() mode with grad enabled the forward
+    is the differentiable graph of autograd.py (CUDA eigen-solver + torch element-wise ops);
   * `norm_scope` / `chunk` attributes control how the ZLayer batch mean (admm_net.py:459) is scoped:
       'batch' (default) = the whole batch of the call, exactly like the reference;
       'chunk'           = independent chunks of `chunk` signals (throughput mode, no coupling);
@@ -188,8 +189,17 @@ class PhiEstADMMNet(nn.Module):
             raise _capi.AdmmnetError(f"eigen-solver reported status {st.value} (QL non-convergence / stream overflow)")
 
     def forward(self, y, b, sigma):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned:
-            warnings.warn("admmnet_b200: forward is an inference fast path; the result is detached from autograd")
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad and self.training:
+            # training: differentiable graph around the CUDA eigen-solver (autograd.py)
+            from .autograd import forward_train
+            src_dev = y.device
+            yd, bd, sd, _ = self._prep(y, b, sigma)
+            out = forward_train(self, yd, bd, sd)
+            return out if src_dev.type == "cuda" else out.to(src_dev)
+        if needs_grad and not self._warned:
+            warnings.warn("admmnet_b200: eval-mode forward is the inference fast path; the result is detached from "
+                          "autograd (call model.train() for the differentiable path)")
             self._warned = True
         src_dev = y.device
         yd, bd, sd, _ = self._prep(y, b, sigma)

@@ -151,6 +151,26 @@ def main():
         if tag == "init_k10":
             phi_for_peaks = phi
 
+    # ------------------------------------------------------------------ gradients (trainPhi.py:167-172 with loss.py:62-98)
+    import loss as ref_loss
+    assert os.path.abspath(ref_loss.__file__).startswith(REF)
+    torch.manual_seed(4)
+    tm = admm_net.PhiEstADMMNet(10, 10, 3, 4).train()
+    perturb_(tm, 10)
+    torch.manual_seed(5)
+    phi_true = torch.view_as_complex(torch.randn(7, 100, 2) * 0.2).to(torch.complex64)
+    crit = ref_loss.PhiAlignmentLoss()
+    out_phi = tm(ty, tb, ts)
+    total, parts = crit(out_phi, phi_true)
+    total.backward()
+    grads = {n_.replace(".", "__"): (p_.grad.numpy() if p_.grad is not None else np.zeros(0, np.float32))
+             for n_, p_ in tm.named_parameters()}
+    np.savez(os.path.join(HERE, "train_grads_k4.npz"), y=y_all, b=b_all, sigma=s_all, K=4, phi_true=phi_true.numpy(),
+             loss=float(total), amplitude_loss=float(parts["amplitude_loss"]), phase_loss=float(parts["phase_loss"]),
+             phi=out_phi.detach().numpy(), **{"grad__" + k_: v_ for k_, v_ in grads.items()},
+             **{"sd__" + k_: v_ for k_, v_ in sd_to_npz(tm.state_dict()).items()})
+    print("train loss", float(total), "params with grad", sum(v_.size > 0 for v_ in grads.values()), "of", len(grads))
+
     # ------------------------------------------------------------------ full ADMMNet (unrolled loop + PeakSearchLayer head)
     torch.manual_seed(3)
     full = admm_net.ADMMNet(10, 10, 3, 3).eval()
