@@ -651,14 +651,24 @@ extern "C" int admmnet_fp32_peak_launch(float* out, int grid, int iters, double*
 }
 
 // ------------------------------------------------------------------------------------ synthetic inputs
+extern "C" int admmnet_generate_dataset(void* y, void* b, float* sigma, double* truth, float* ser, int B, int Nb, int Nd,
+                                        int L, double snr_w_lo_db, double snr_w_hi_db, double snr_demod_db,
+                                        unsigned long long seed, void* stream);
 extern "C" int admmnet_generate(void* y, void* b, float* sigma, double* truth, int B, int Nb, int Nd, int L,
                                 double snr_w_db, double snr_demod_db, unsigned long long seed, void* stream) {
+    return admmnet_generate_dataset(y, b, sigma, truth, nullptr, B, Nb, Nd, L, snr_w_db, snr_w_db, snr_demod_db, seed,
+                                    stream);
+}
+extern "C" int admmnet_generate_dataset(void* y, void* b, float* sigma, double* truth, float* ser, int B, int Nb, int Nd,
+                                        int L, double snr_w_db, double snr_w_hi_db, double snr_demod_db,
+                                        unsigned long long seed, void* stream) {
     if (!y || !b || !sigma) return fail(ADMMNET_ERR_ARG, "null pointer");
     if (B <= 0 || Nb < 1 || Nd < 1 || Nb * Nd > 256 || L < 1 || L > GEN_MAXL)
         return fail(ADMMNET_ERR_ARG, "need B > 0, Nb*Nd <= 256, 1 <= L <= 8");
     GenArgs a;
-    a.y = (float2*)y; a.b = (float2*)b; a.sigma = sigma; a.truth = truth;
-    a.B = B; a.Nb = Nb; a.Nd = Nd; a.L = L; a.snr_w_db = snr_w_db; a.snr_demod_db = snr_demod_db; a.seed = seed;
+    a.y = (float2*)y; a.b = (float2*)b; a.sigma = sigma; a.truth = truth; a.ser = ser;
+    a.B = B; a.Nb = Nb; a.Nd = Nd; a.L = L; a.snr_w_db = snr_w_db; a.snr_w_hi_db = snr_w_hi_db;
+    a.snr_demod_db = snr_demod_db; a.seed = seed;
     const long long nthreads = (long long)B * 32;
     prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
     k_generate<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);

@@ -49,8 +49,9 @@ struct GenArgs {
     float2* b;        // [B][n]
     float* sigma;     // [B]
     double* truth;    // optional [B][L][4]: tau, f, Re C, Im C
+    float* ser;       // optional [B]: symbol error rate in percent (generate_data.py:220)
     int B, Nb, Nd, L;
-    double snr_w_db, snr_demod_db;
+    double snr_w_db, snr_w_hi_db, snr_demod_db;   // noise SNR drawn uniformly in [snr_w_db, snr_w_hi_db) when hi > lo (:164)
     unsigned long long seed;
 };
 
@@ -70,10 +71,13 @@ __global__ void __launch_bounds__(256) k_generate(GenArgs a) {
             double* t = a.truth + ((size_t)w * L + l) * 4;
             t[0] = tau[l]; t[1] = f[l]; t[2] = cr[l]; t[3] = ci[l];
         }
+    double snr_w = a.snr_w_db;
+    if (a.snr_w_hi_db > a.snr_w_db) snr_w += (a.snr_w_hi_db - a.snr_w_db) * g0.uniform();
     const double npow = 1.0 / pow(10.0, a.snr_demod_db / 10.0);               // awgn on unit-power PSK
     // per-element work: lane handles elements lane, lane+32, ... with its own stream
     Philox g(a.seed, (uint64_t)w * 64 + 1 + lane);
     double ynorm2 = 0.0, er2 = 0.0;
+    int nerr = 0;
     double2 yv[8], bv[8], wv[8];
     for (int e = 0; e < 8; ++e) {
         const int i = lane + 32 * e;
@@ -106,13 +110,15 @@ __global__ void __launch_bounds__(256) k_generate(GenArgs a) {
         ynorm2 += yr * yr + yi * yi;
         const double bden = b_re * b_re + b_im * b_im;                         // |e/b|^2 = |e|^2/|b|^2
         er2 += (e_re * e_re + e_im * e_im) / bden;
+        nerr += (sqrt(e_re * e_re + e_im * e_im) > 1e-10);
         yv[e] = make_double2(yr, yi);
         bv[e] = make_double2(b_re, b_im);
         wv[e] = g.normal2();
     }
     ynorm2 = warp_sum(ynorm2);
     er2 = warp_sum(er2);
-    const double w_var = ynorm2 / (pow(10.0, a.snr_w_db / 10.0) * n);          // :166
+    nerr = (int)warp_sum((double)nerr);
+    const double w_var = ynorm2 / (pow(10.0, snr_w / 10.0) * n);               // :166
     const double amp = sqrt(w_var) * sqrt(0.5);
     for (int e = 0; e < 8; ++e) {
         const int i = lane + 32 * e;
@@ -121,6 +127,7 @@ __global__ void __launch_bounds__(256) k_generate(GenArgs a) {
         a.b[(size_t)w * n + i] = make_float2((float)bv[e].x, (float)bv[e].y);
     }
     if (lane == 0) a.sigma[w] = (float)(sqrt(er2) + 1.0);                      // sigma = ||e/b|| + 1  (:171)
+    if (lane == 0 && a.ser) a.ser[w] = (float)(100.0 * nerr / n);
 }
 
 }  // namespace admmnet

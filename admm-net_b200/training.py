@@ -33,3 +33,83 @@ def train_step(model, criterion, optimizer, y, b, sigma, phi_true, max_norm=1.0,
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
     optimizer.step()
     return loss.detach(), parts
+
+
+def make_optimizer(model, lr=5e-3, weight_decay=1e-3):
+    """trainPhi.py:100-118: AdamW on the four layer lists at lr/2, cosine warm restarts (T_0=10, T_mult=2)."""
+    admm_params = [p for name, p in model.named_parameters()
+                   if any(prefix in name for prefix in ("phiLayers", "hLayers", "gLayers", "zLayers"))]
+    optimizer = torch.optim.AdamW([{"params": admm_params, "lr": lr * 0.5}], lr=lr, weight_decay=weight_decay)
+    scheduler = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(optimizer, T_0=10, T_mult=2, eta_min=1e-6)
+    return optimizer, scheduler
+
+
+def _batches(tensors, batch_size, order, rank, world):
+    """Each global batch of `batch_size` samples is split evenly over the ranks (data parallel); the ZLayer batch
+    mean (admm_net.py:459) is then taken per rank, i.e. over batch_size/world samples — the statistic
+    torch's DistributedDataParallel would also give the reference."""
+    from .sharding import shard_range
+    n = order.numel()
+    for lo in range(0, n, batch_size):
+        idx = order[lo:min(lo + batch_size, n)]
+        a, b = shard_range(idx.numel(), rank, world)
+        if b > a:
+            yield tuple(t[idx[a:b]] for t in tensors)
+
+
+def fit(model, train, val, config, device="cuda", group=None, log=print):
+    """trainPhi.py:148-261: epochs of (train, validate, scheduler.step, checkpoint-on-best, early stopping with
+    patience 10).  `train`/`val` are the tuples of dataset.load_split; config keys as in trainPhi.py:13-43
+    (batch_size, epochs, lr, weight_decay, checkpoint_dir).  Under torch.distributed every rank calls fit with the
+    same data and seed; gradients are averaged with one flat all-reduce per step."""
+    import os
+
+    from .autograd import PhiAlignmentLoss
+    from .dataset import load_checkpoint, save_checkpoint
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    criterion = PhiAlignmentLoss()
+    optimizer, scheduler = make_optimizer(model, config.get("lr", 5e-3), config.get("weight_decay", 1e-3))
+    start_epoch, best_val, patience, bad = 0, float("inf"), config.get("patience", 10), 0
+    ck_path = os.path.join(config["checkpoint_dir"], "best_model.pth") if config.get("checkpoint_dir") else None
+    if ck_path and os.path.exists(ck_path):
+        start_epoch, best_val, _ = load_checkpoint(ck_path, model, optimizer, scheduler, map_location=device)
+    history = {"train_loss": [], "val_loss": [], "tau_rmse": [], "f_rmse": [], "lr": []}
+    sel = lambda t: (t[0], t[1], t[6], t[7])                 # y, b, sigma, phi_true
+    gen = torch.Generator().manual_seed(config.get("seed", 0))
+    bs = config.get("batch_size", 256)
+    for epoch in range(start_epoch, config.get("epochs", 1000)):
+        order = torch.randperm(train[0].shape[0], generator=gen)
+        tot, nb = torch.zeros((), device=device), 0
+        for y, b, s, pt in _batches(sel(train), bs, order, rank, world):
+            y, b, s, pt = (t.to(device, non_blocking=True) for t in (y, b, s, pt))
+            loss, _ = train_step(model, criterion, optimizer, y, b, s, pt, group=group)
+            tot += loss
+            nb += 1
+        train_loss = float(tot) / max(nb, 1)
+        model.eval()
+        vt, vb = torch.zeros((), device=device), 0
+        with torch.no_grad():
+            for y, b, s, pt in _batches(sel(val), bs, torch.arange(val[0].shape[0]), rank, world):
+                y, b, s, pt = (t.to(device, non_blocking=True) for t in (y, b, s, pt))
+                vt += criterion(model(y, b, s), pt)[0]
+                vb += 1
+        stats = torch.stack([vt, torch.tensor(float(vb), device=device)])
+        if distributed:
+            dist.all_reduce(stats, group=group)
+        val_loss = float(stats[0] / stats[1].clamp(min=1))
+        history["train_loss"].append(train_loss)
+        history["val_loss"].append(val_loss)
+        history["lr"].append(optimizer.param_groups[0]["lr"])
+        log(f"epoch {epoch + 1}: train {train_loss:.6f}  val {val_loss:.6f}  lr {history['lr'][-1]:.2e}")
+        scheduler.step()
+        if val_loss < best_val:
+            best_val, bad = val_loss, 0
+            if ck_path and rank == 0:
+                save_checkpoint(ck_path, epoch, model, optimizer, scheduler, best_val, config, history)
+        else:
+            bad += 1
+        if bad >= patience:
+            break
+    return history

@@ -135,6 +135,11 @@ int admmnet_peak_head(const void* phi, int B, int n, int L, const float* head_pa
  * ------------------------------------------------------------------------------------------- */
 int admmnet_generate(void* y, void* b, float* sigma, double* truth, int B, int Nb, int Nd, int L, double snr_w_db,
                      double snr_demod_db, unsigned long long seed, void* stream);
+/* dataset variant (DatasetGeneratorCreatePhi, generate_data.py:410-463): the noise SNR of every signal is drawn
+ * uniformly from [snr_w_lo_db, snr_w_hi_db) and the symbol error rate (percent) is written to ser[B] (optional). */
+int admmnet_generate_dataset(void* y, void* b, float* sigma, double* truth, float* ser, int B, int Nb, int Nd, int L,
+                             double snr_w_lo_db, double snr_w_hi_db, double snr_demod_db, unsigned long long seed,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): per-kernel CUDA-event timing of the launches issued between

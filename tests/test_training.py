@@ -1,6 +1,7 @@
 """Training path: the differentiable graph and its gradients against the reference's own
 autograd (tests/golden/train_grads_k4.npz, written by tests/golden/make_golden.py from trainPhi.py's loss/backward),
 and the flat gradient all-reduce on two gloo ranks."""
+import json
 import os
 import sys
 
@@ -63,7 +64,7 @@ def test_training_graph_gradients_match_reference_cpu():
     loss, parts = PhiAlignmentLoss()(phi, pt)
     loss.backward()
     assert np.abs(phi.detach().numpy() - z["phi"]).max() < 1e-4 * np.abs(z["phi"]).max()
-    assert abs(float(loss) - float(z["loss"])) < 1e-4 * float(z["loss"])
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-4 * float(z["loss"])
     assert abs(float(parts["phase_loss"]) - float(z["phase_loss"])) < 1e-4 * float(z["phase_loss"])
     _compare_grads(model, grads, 2e-3)
 
@@ -123,7 +124,7 @@ def test_training_gradients_match_reference_gpu():
     loss, _ = PhiAlignmentLoss()(phi, pt)
     loss.backward()
     assert np.abs(phi.detach().cpu().numpy() - z["phi"]).max() < 1e-4 * np.abs(z["phi"]).max()
-    assert abs(float(loss) - float(z["loss"])) < 1e-4 * float(z["loss"])
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-4 * float(z["loss"])
     worst = _compare_grads(model, grads, 5e-3)
     print("worst relative gradient error", worst)
 
@@ -146,3 +147,105 @@ def test_train_step_lowers_the_loss_gpu():
     model.train()
     slow = model(y, b, s).detach()
     assert float((fast - slow).abs().max() / slow.abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------ dataset / checkpoint formats
+def _fake_split(d, n=6, nn=100, L=3, with_phi=True):
+    rng = np.random.default_rng(0)
+    os.makedirs(d)
+    arrs = {"y_real": (n, nn), "y_imag": (n, nn), "b_real": (n, nn), "b_imag": (n, nn), "tau": (n, L), "f": (n, L),
+            "C_real": (n, L), "C_imag": (n, L), "sigma": (n,), "ser": (n,)}
+    if with_phi:
+        arrs.update({"phi_real": (n, nn), "phi_imag": (n, nn)})
+    out = {k: rng.standard_normal(s).astype(np.float32) for k, s in arrs.items()}
+    out["L_true"] = np.full((n,), L, dtype=np.int32)
+    for k, v in out.items():
+        np.save(os.path.join(d, k + ".npy"), v)
+    return out
+
+
+def test_load_split_reads_the_reference_layout(tmp_path):
+    from admmnet_b200.dataset import load_split
+    raw = _fake_split(str(tmp_path / "train"))
+    y, b, tau, f, C, L_true, sigma, phi = load_split(str(tmp_path), "train")
+    assert y.dtype == torch.complex64 and L_true.dtype == torch.int64 and sigma.dtype == torch.float32
+    assert np.array_equal(y.numpy(), raw["y_real"] + 1j * raw["y_imag"])
+    assert np.array_equal(phi.numpy(), raw["phi_real"] + 1j * raw["phi_imag"])
+    assert np.array_equal(C.numpy(), raw["C_real"] + 1j * raw["C_imag"])
+    _fake_split(str(tmp_path / "val"), with_phi=False)          # base-class datasets carry no phi
+    assert len(load_split(str(tmp_path), "val")) == 7
+    with pytest.raises(ValueError):
+        load_split(str(tmp_path), "test")
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    from admmnet_b200.dataset import load_checkpoint, save_checkpoint
+    from admmnet_b200.training import make_optimizer
+    z, sd, _ = _load()
+    model = _model(sd, int(z["K"]))
+    opt, sch = make_optimizer(model)
+    assert opt.param_groups[0]["lr"] == 2.5e-3 and len(opt.param_groups[0]["params"]) == len(list(model.parameters()))
+    path = str(tmp_path / "best_model.pth")
+    save_checkpoint(path, 4, model, opt, sch, 0.25, {"lr": 5e-3}, {"train_loss": [1.0]})
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_val_loss",
+                       "config", "history"}                       # trainPhi.py:238-246
+    assert set(ck["model_state_dict"]) == set(sd)               # the reference's own state_dict keys
+    fresh = _model({k: torch.zeros_like(v) for k, v in sd.items()}, int(z["K"]))
+    opt2, sch2 = make_optimizer(fresh)
+    start, best, _ = load_checkpoint(path, fresh, opt2, sch2)
+    assert (start, best) == (5, 0.25)
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_batches_split_every_global_batch_over_the_ranks():
+    from admmnet_b200.training import _batches
+    x = torch.arange(10)
+    order = torch.arange(10)
+    got = [[t[0].tolist() for t in _batches((x,), 4, order, r, 2)] for r in range(2)]
+    assert got[0] == [[0, 1], [4, 5], [8]] and got[1] == [[2, 3], [6, 7], [9]]
+
+
+@pytest.mark.gpu
+def test_generate_dataset_writes_reference_format_gpu(tmp_path):
+    from admmnet_b200.dataset import FIELDS, generate_dataset, load_split
+    from oracle import classic_oracle
+    generate_dataset(str(tmp_path), total_samples=200, seed=3)
+    for split, n in (("train", 140), ("val", 30), ("test", 30)):
+        for k in FIELDS:
+            a = np.load(tmp_path / split / f"{k}.npy")
+            assert a.shape[0] == n and a.dtype == (np.int32 if k == "L_true" else np.float32), (split, k)
+    y, b, tau, f, C, L_true, sigma, phi = load_split(str(tmp_path), "train")
+    assert float(tau.min()) >= 0.1 and float(tau.max()) <= 0.9 and float(f.abs().max()) <= 0.4
+    assert np.allclose(np.abs(b.numpy()), 1.0, atol=1e-6)
+    ser = np.load(tmp_path / "train" / "ser.npy")
+    assert ((ser > 0) == (sigma.numpy() > 1.0)).all() and 0 < ser.mean() < 30          # QPSK at 7 dB: a few percent
+    # labels are the classical solver's phi (generate_data.py:454)
+    for i in (0, 57, 139):
+        ref = classic_oracle.admm_for_us(y[i].numpy().astype(np.complex128), b[i].numpy().astype(np.complex128), 10, 10,
+                                         1, float(sigma[i]), {"eta_abs": 1e-7, "eta_rel": 1e-7, "max_iter": 100})[0]
+        assert np.abs(phi[i].numpy() - ref).max() < 2e-6 * np.abs(ref).max()
+    # the noise SNR is drawn per signal from [5, 25) dB: residual power spans the range
+    info = json.load(open(tmp_path / "dataset_config.json"))
+    assert info["train_samples"] == 140 and info["snr_range"] == [5, 25]
+
+
+@pytest.mark.gpu
+def test_fit_trains_checkpoints_and_resumes_gpu(tmp_path):
+    from admmnet_b200.admm_net import PhiEstADMMNet
+    from admmnet_b200.dataset import generate_dataset, load_split
+    from admmnet_b200.training import fit
+    generate_dataset(str(tmp_path / "data"), total_samples=160, seed=1)
+    train, val = load_split(str(tmp_path / "data"), "train"), load_split(str(tmp_path / "data"), "val")
+    os.makedirs(tmp_path / "ck")
+    cfg = {"batch_size": 56, "epochs": 3, "lr": 5e-3, "weight_decay": 1e-3, "checkpoint_dir": str(tmp_path / "ck")}
+    torch.manual_seed(0)
+    model = PhiEstADMMNet(10, 10, 3, 3).cuda()
+    hist = fit(model, train, val, cfg, log=lambda *_: None)
+    assert len(hist["train_loss"]) == 3 and hist["train_loss"][-1] < hist["train_loss"][0]
+    ck = torch.load(tmp_path / "ck" / "best_model.pth", weights_only=False)
+    assert ck["best_val_loss"] == min(hist["val_loss"])
+    cfg["epochs"] = ck["epoch"] + 2
+    hist2 = fit(PhiEstADMMNet(10, 10, 3, 3).cuda(), train, val, cfg, log=lambda *_: None)   # resumes after the best epoch
+    assert len(hist2["train_loss"]) == 1
