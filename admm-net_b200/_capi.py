@@ -28,6 +28,7 @@ _PROTOS = {
     "peak_search_points": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "admmnet_head_param_count": (_i, [_i, _i]),
     "admmnet_peak_head": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "admmnet_arrow_eigh": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "admmnet_generate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, C.c_ulonglong, _vp]),
     "admmnet_generate_dataset": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _d, _d, _d, C.c_ulonglong, _vp]),
     "admmnet_profile_begin": (_i, []),

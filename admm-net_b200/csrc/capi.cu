@@ -7,6 +7,7 @@
 
 #include "../../include/admmnet_b200.h"
 #include "net_kernels.cu"
+#include "arrow_kernels.cu"
 #include "classic_kernels.cu"
 #include "peak_kernels.cu"
 #include "gen_kernels.cu"
@@ -30,8 +31,8 @@ static int fail(int code, const std::string& msg) {
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
 // Process-global, not thread safe; off by default (then the only cost is one branch per launch).
 namespace prof {
-enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, NKINDS };
-static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge"};
+enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, ARROW, NKINDS };
+static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge", "k_arrow"};
 struct Rec { int kind; cudaEvent_t a, b; };
 static bool on = false;
 static std::vector<Rec> recs;
@@ -99,11 +100,22 @@ struct Ws {
     float *Zr, *Zr2, *lam, *dT, *eT, *h_cur, *r, *mean;
     double* rho;
     int *nrot, *status;
+    int* handled;      // [chunk] per slot: 1 = layer-0 signal solved by k_arrow
     double* rsum;
     size_t bytes;
 };
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
-constexpr int NSLOT = 2;
+constexpr int NSLOT_MAX = 8;
+// number of chunk lanes = scratch slots (chunks of one layer in flight); ADMMNET_NSLOT overrides (1..8)
+static int nslot_value() {
+    static const int v = [] {
+        const char* e = getenv("ADMMNET_NSLOT");
+        const int x = e ? atoi(e) : 2;
+        return x < 1 ? 1 : (x > NSLOT_MAX ? NSLOT_MAX : x);
+    }();
+    return v;
+}
+#define NSLOT (nslot_value())
 constexpr int TR_MAX = 88;   // largest trailing block handed to a later tridiagonalisation stage
 // orders at which the trailing block is compacted and handed to the next (smaller, higher-occupancy) stage
 inline int next_stage_order(int d) {
@@ -152,6 +164,7 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     w.h_cur = (float*)take((size_t)B * n * sizeof(float));
     w.r = (float*)take((size_t)B * sizeof(float));
     w.nrot = (int*)take((size_t)NSLOT * C * sizeof(int));
+    w.handled = (int*)take((size_t)NSLOT * C * sizeof(int));
     w.rsum = (double*)take((size_t)(K + 1) * sizeof(double));
     w.mean = (float*)take((size_t)(K + 1) * sizeof(float));
     w.status = (int*)take(sizeof(int));
@@ -189,7 +202,7 @@ inline TearSpec dc_tears(int d, int B) {
 }
 
 // later tridiagonalisation stages on the compacted trailing block (no-op when stage 1 did everything)
-int launch_head2(const Ws& w, int B, int d, cudaStream_t st) {
+int launch_head2(const Ws& w, int B, int d, cudaStream_t st, const int* skip = nullptr) {
     int dcur = next_stage_order(d);          // order handed over by k_head
     if (!dcur) return 0;
     const size_t tr_sz = (size_t)B * TR_MAX * TR_MAX;
@@ -200,6 +213,7 @@ int launch_head2(const Ws& w, int B, int d, cudaStream_t st) {
         Head2Args h;
         h.Tin = bufs[which]; h.Tout = bufs[which ^ 1]; h.GV = w.GV; h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
         h.B = B; h.d = d; h.d2 = dcur; h.ld2 = dcur | 1; h.k0 = d - dcur; h.k_stop = nx ? dcur - nx : dcur - 1;
+        h.skip = skip;
         prof::Scope pscope(prof::HEAD2, st);
         if (dcur > 64) {
             const size_t sm = head2_smem_bytes<256, 128>(h.d2, h.ld2);
@@ -220,7 +234,7 @@ int launch_head2(const Ws& w, int B, int d, cudaStream_t st) {
 // the three eigen-solver launches after the tridiagonal form is in the workspace
 int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk, int with_c, float2* U_out,
                     float* lamp_out, int* status, cudaStream_t st, cudaStream_t qst = nullptr,
-                    cudaEvent_t ev_in = nullptr, cudaEvent_t ev_out = nullptr) {
+                    cudaEvent_t ev_in = nullptr, cudaEvent_t ev_out = nullptr, const int* skip = nullptr) {
     const bool side = qst != nullptr;
     if (side) {   // k_ql on a high-priority side stream: it is latency bound and co-resides with other kernels
         CK(cudaEventRecord(ev_in, st));
@@ -233,7 +247,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
-                                                                         status, dc_tears(d, B), w.rho);
+                                                                         status, dc_tears(d, B), w.rho, skip);
         CK(cudaGetLastError());
     }
     if (side) {
@@ -244,7 +258,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         const size_t sm = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (4 * ((d + 3) / 4)) * sizeof(float);
         CK(cudaFuncSetAttribute(k_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::ROT, st);
-        k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr);
+        k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
         CK(cudaGetLastError());
     }
     // divide & conquer merges, leaves -> root; Z ping-pongs between the two scratch buffers
@@ -260,7 +274,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
             // tears t-half and t+half.  The ranges of a level partition [0,d): one launch handles all (<= 4).
             MergeArgs m;
             m.Zin = zb[cur]; m.Zout = zb[cur ^ 1]; m.lam = w.lam; m.rho = w.rho; m.status = status;
-            m.B = B; m.d = d; m.nr = 0;
+            m.B = B; m.d = d; m.nr = 0; m.skip = skip;
             for (int i = 0; i < ts.n; ++i) {
                 if ((i + 1) % step != half) continue;
                 const int lo = (i + 1) - half, hi = (i + 1) + half;
@@ -283,7 +297,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         TailArgs t;
         t.Zr = zfinal; t.GV = w.GV; t.tau = w.tau; t.lam = w.lam; t.phi_cur = w.phi_cur; t.h_cur = w.h_cur;
         t.Pk = Pk; t.r_out = w.r; t.U_out = U_out; t.lamp_out = lamp_out;
-        t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c;
+        t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c; t.skip = skip;
         const size_t sm = tail_smem_bytes(d, t.ldu);
         prof::Scope pscope(prof::TAIL, st);
         if (d <= 104) {
@@ -313,6 +327,7 @@ static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0
     c.dT += (size_t)slot * C * d;
     c.eT += (size_t)slot * C * d;
     c.nrot += (size_t)slot * C;
+    c.handled += (size_t)slot * C;
     c.Zp += (size_t)off * npk;
     c.GV += (size_t)off * npk;
     c.phi_cur += (size_t)off * n;
@@ -344,8 +359,8 @@ extern "C" int admmnet_ws_scalars(void* ws, size_t ws_bytes, int B, int chunk, i
 namespace {
 struct Lanes {
     bool init = false;
-    cudaStream_t L[NSLOT], Q[NSLOT];
-    cudaEvent_t evH[NSLOT], evQ[NSLOT], evDone[NSLOT], evStart, evMean, evEnd;
+    cudaStream_t L[NSLOT_MAX], Q[NSLOT_MAX];
+    cudaEvent_t evH[NSLOT_MAX], evQ[NSLOT_MAX], evDone[NSLOT_MAX], evStart, evMean, evEnd;
 };
 Lanes g_lanes[16];
 int get_lanes(Lanes** out) {
@@ -404,6 +419,24 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     h.tau = w.tau; h.dT = w.dT; h.eT = w.eT;
     h.B = Bc; h.n = n; h.d = d; h.ld = d | 1; h.first = (k == 0);
     h.Ttr = w.Ttr; h.k1 = stage1_steps(d);
+    // layer 0: the matrix is an arrowhead; k_arrow solves it directly and the general pipeline only sees the
+    // signals it declined (handled[sig] == 0).  ADMMNET_ARROW=0 switches the shortcut off.
+    static const bool use_arrow = !(getenv("ADMMNET_ARROW") && atoi(getenv("ADMMNET_ARROW")) == 0);
+    const int* skip = nullptr;
+    if (h.first && use_arrow) {
+        ArrowArgs aa;
+        aa.y = h.y; aa.b = h.b; aa.sigma = h.sigma; aa.h_in = nullptr; aa.phi_in = nullptr; aa.c0_in = nullptr;
+        aa.Zp = w.Zp; aa.GV = w.GV; aa.phi_cur = w.phi_cur; aa.h_cur = w.h_cur; aa.Pk = h.Pk; aa.r_out = w.r;
+        aa.handled = w.handled; aa.lam_out = nullptr; aa.U_out = nullptr;
+        aa.B = Bc; aa.n = n; aa.d = d; aa.ldu = 4 * ((d + 3) / 4);
+        const size_t sma = arrow_smem_bytes(d, aa.ldu);
+        CK(cudaFuncSetAttribute(k_arrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+        prof::Scope pscope(prof::ARROW, st);
+        k_arrow<<<Bc, AR_NT, sma, st>>>(aa);
+        CK(cudaGetLastError());
+        skip = w.handled;
+    }
+    h.skip = skip;
     const size_t sm = head_smem_bytes(d, h.ld);
     CK(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     {
@@ -411,8 +444,8 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
         k_head<<<Bc, 256, sm, st>>>(h);
     }
     CK(cudaGetLastError());
-    if (int e = launch_head2(w, Bc, d, st)) return e;
-    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out);
+    if (int e = launch_head2(w, Bc, d, st, skip)) return e;
+    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out, skip);
 }
 
 extern "C" int admmnet_reset_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream) {
@@ -527,6 +560,24 @@ extern "C" int admmnet_status(void* ws, size_t ws_bytes, int B, int chunk, int n
     if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
     CK(cudaMemcpyAsync(status_host, w.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ arrowhead tap
+extern "C" int admmnet_arrow_eigh(const float* h, const void* phi, const float* c0, int B, int n, float* evals,
+                                  void* evecs, int* handled, void* stream) {
+    if (!h || !phi || !c0 || !evals || !handled) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (B <= 0 || n < 2 || n > 127) return fail(ADMMNET_ERR_ARG, "need B > 0 and 2 <= n <= 127");
+    ArrowArgs aa;
+    aa.y = nullptr; aa.b = nullptr; aa.sigma = nullptr; aa.h_in = h; aa.phi_in = (const float2*)phi; aa.c0_in = c0;
+    aa.Zp = nullptr; aa.GV = nullptr; aa.phi_cur = nullptr; aa.h_cur = nullptr; aa.Pk = nullptr; aa.r_out = nullptr;
+    aa.handled = handled; aa.lam_out = evals; aa.U_out = (float2*)evecs;
+    aa.B = B; aa.n = n; aa.d = n + 1; aa.ldu = 4 * ((n + 1 + 3) / 4);
+    const size_t sma = arrow_smem_bytes(aa.d, aa.ldu);
+    CK(cudaFuncSetAttribute(k_arrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+    prof::Scope pscope(prof::ARROW, (cudaStream_t)stream);
+    k_arrow<<<B, AR_NT, sma, (cudaStream_t)stream>>>(aa);
+    CK(cudaGetLastError());
     return 0;
 }
 

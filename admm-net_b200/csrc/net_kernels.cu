@@ -348,6 +348,7 @@ struct HeadArgs {
     float2* Ttr;         // [B][d2*d2] trailing block handed to k_head2 (k1 < d-1)
     int B, n, d, ld, first;
     int k1;              // Householder steps done here; d-1 = everything
+    const int* skip;     // optional [B]: 1 = signal already handled by k_arrow (layer 0)
 };
 
 __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
     HeadSmem s = carve_head(smem_raw, d, ld);
     const int tid = threadIdx.x;
     const int sig = blockIdx.x;
+    if (a.skip && a.skip[sig]) return;
     const int npk = d * (d + 1) / 2;
     const float* __restrict__ P = a.Pk;
     float2* Zp = a.Zp + (size_t)sig * npk;
@@ -495,6 +497,7 @@ struct Head2Args {
     float* dT;
     float* eT;
     int B, d, d2, ld2, k0, k_stop;
+    const int* skip;
 };
 template <int NT, int PSTR>
 __host__ __device__ inline size_t head2_smem_bytes(int d2, int ld2) {
@@ -517,6 +520,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 3) k_head2(Head2Args a) {
     float* ee = dd + 128;
     S.red = nullptr;
     const int sig = blockIdx.x;
+    if (a.skip && a.skip[sig]) return;
     const float2* T = a.Tin + (size_t)sig * d2 * d2;
     for (int idx = threadIdx.x; idx < d2 * d2; idx += NT) {
         const int c = idx / d2, r = idx % d2;
@@ -591,13 +595,13 @@ struct TearSpec {
 __global__ void __launch_bounds__(QL_THREADS)
 k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, float* __restrict__ lam,
      float2* __restrict__ rot, int rcap, int* __restrict__ nrot, int* __restrict__ status, TearSpec tears,
-     double* __restrict__ rho_out) {
+     double* __restrict__ rho_out, const int* __restrict__ skip) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sd = reinterpret_cast<double*>(smem_raw);
     double* se = sd + (size_t)d * QL_THREADS;
     const int t = threadIdx.x;
     const int sig = blockIdx.x * QL_THREADS + t;
-    const bool valid = sig < B;
+    const bool valid = sig < B && !(skip && skip[sig]);
 #define D_(i) sd[(i) * QL_THREADS + t]
 #define E_(i) se[(i) * QL_THREADS + t]
     double anorm = 0.0;
@@ -649,19 +653,13 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
                 phase = DONE;
             } else {                // Wilkinson shift, sweep i = m-1 .. l
                 // g = d[m] - d[l] + e/(t + sign(t) sqrt(t^2+1)), t = delta/(2e)  ==  2e^2/(delta + sign(delta) hypot(delta, 2e))
-                const double el = E_(l), delta = D_(l + 1) - D_(l);
-                const double x = delta * delta + 4.0 * el * el;
-                double hyp;
-                if (x > 1e-30 && x < 1e30) {
-                    double ri = (double)rsqrtf((float)x);
-                    ri = ri * (1.5 - 0.5 * x * ri * ri);
-                    ri = ri * (1.5 - 0.5 * x * ri * ri);
-                    hyp = x * ri;
-                } else {
-                    hyp = sqrt(x);
-                }
-                const double den = delta + copysign(hyp, delta);
-                g = D_(m) - D_(l) + (2.0 * el * el) / den;
+                // The shift only steers convergence (any value is a valid QL step), so it is formed in fp32.
+                const double dl0 = D_(l);
+                const float el = (float)E_(l), delta = (float)(D_(l + 1) - dl0);
+                const float hyp = sqrtf(fmaf(delta, delta, 4.f * el * el));
+                const float den = delta + copysignf(hyp, delta);
+                const float corr = den != 0.f ? __fdividef(2.f * el * el, den) : 0.f;
+                g = D_(m) - dl0 + (double)corr;
                 s = 1.0; c = 1.0; p = 0.0;
                 i = m - 1;
                 hdr = nrec++;
@@ -682,11 +680,11 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
                 nm2 = nm1; nm1 = i + 1;
                 end_sweep = true;
             } else {
-                // 1/sqrt(h2): fp32 seed + two fp64 Newton steps instead of a sqrt and two divisions
+                // 1/sqrt(h2): fp32 seed (2^-22) + one fp64 Newton step (-> 1e-13) instead of a sqrt and two divisions;
+                // (c, s) leave as fp32 and the d/e recurrences only need to stay well below fp32 rounding
                 double rinv;
                 if (h2 > 1e-30 && h2 < 1e30) {
                     rinv = (double)rsqrtf((float)h2);
-                    rinv = rinv * (1.5 - 0.5 * h2 * rinv * rinv);
                     rinv = rinv * (1.5 - 0.5 * h2 * rinv * rinv);
                 } else {
                     rinv = 1.0 / sqrt(h2);
@@ -765,13 +763,15 @@ __device__ __forceinline__ void rot4(float4& out, float4& cy, const float4 zi, c
 // 4l..4l+3, so one rotation is one 128-bit load, 16 FP ops and one 128-bit store per lane, and one
 // broadcast load of (c,s) feeds four independent chains.  Output: Z^T, i.e. Zt[c][r] row-major [d][d].
 __global__ void __launch_bounds__(ROT_THREADS)
-k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zt) {
+k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zt,
+      const int* __restrict__ skip) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* stage = reinterpret_cast<float2*>(smem_raw);                  // [2][ROT_STAGE]
     float* z = reinterpret_cast<float*>(stage + 2 * ROT_STAGE);           // [d][ldr]
     const int ldr = 4 * ((d + 3) / 4);
     const int lane = threadIdx.x;
     const int sig = blockIdx.x;
+    if (skip && skip[sig]) return;
     const float2* src = rot + (size_t)sig * rcap;
     const int total = nrot[sig];
     for (int idx = lane; idx < d * ldr; idx += 32) z[idx] = 0.f;
@@ -863,6 +863,7 @@ struct MergeArgs {
     int* status;
     int B, d, nr;
     int ra[MG_MAXR], rp[MG_MAXR], rb[MG_MAXR], rt[MG_MAXR];   // range [a,b), tear row p, tear index
+    const int* skip;
 };
 __host__ __device__ inline size_t merge_smem_bytes(int d) {
     const int ldr = 4 * ((d + 3) / 4);
@@ -964,6 +965,7 @@ __global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
     int* nrotl = ib + 896;        // [1]
     const int tid = threadIdx.x;
     const int sig = blockIdx.x;
+    if (a.skip && a.skip[sig]) return;
     const float* Zg = a.Zin + (size_t)sig * d * d;
     float* Zo = a.Zout + (size_t)sig * d * d;
     float* lam = a.lam + (size_t)sig * d;
@@ -1207,6 +1209,71 @@ __global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
     }
 }
 
+// G = U diag(l') U^H on 4x4 register tiles of the lower triangle, written packed to GV; returns this thread's share
+// of ||G - C||_F^2 (C = [[diag(h), phi],[phi^H, c1z]]) when with_c.  U is column-major [k][ldu] in shared memory.
+template <int NT>
+__device__ __forceinline__ float rebuild_lower(const float2* __restrict__ U, int ldu, const float* __restrict__ lamp,
+                                               int d, int n, float2* __restrict__ GV, const float* __restrict__ hs,
+                                               const float2* __restrict__ phis, float c1z, bool with_c) {
+    const int tid = threadIdx.x;
+    const int nt1 = (d + 3) / 4;
+    const int ntiles = nt1 * (nt1 + 1) / 2;
+    float rsq = 0.f;
+    for (int t = tid; t < ntiles; t += NT) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        float2 acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int yv = 0; yv < 4; ++yv) acc[x][yv] = make_float2(0.f, 0.f);
+        const float4* Ua = reinterpret_cast<const float4*>(U + 4 * ti);
+        const float4* Ub = reinterpret_cast<const float4*>(U + 4 * tj);
+        const int ld4 = ldu / 2;   // float4 stride per column
+        for (int k = 0; k < d; ++k) {
+            const float lp = lamp[k];
+            const float4 a01 = Ua[(size_t)k * ld4], a23 = Ua[(size_t)k * ld4 + 1];
+            const float4 b01 = Ub[(size_t)k * ld4], b23 = Ub[(size_t)k * ld4 + 1];
+            const float2 av[4] = {make_float2(lp * a01.x, lp * a01.y), make_float2(lp * a01.z, lp * a01.w),
+                                  make_float2(lp * a23.x, lp * a23.y), make_float2(lp * a23.z, lp * a23.w)};
+            const float2 bv[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y),
+                                  make_float2(b23.z, b23.w)};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int yv = 0; yv < 4; ++yv) {
+                    acc[x][yv].x = fmaf(av[x].x, bv[yv].x, acc[x][yv].x);
+                    acc[x][yv].x = fmaf(av[x].y, bv[yv].y, acc[x][yv].x);
+                    acc[x][yv].y = fmaf(av[x].y, bv[yv].x, acc[x][yv].y);
+                    acc[x][yv].y = fmaf(-av[x].x, bv[yv].y, acc[x][yv].y);
+                }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int i = 4 * ti + x;
+            if (i >= d) continue;
+#pragma unroll
+            for (int yv = 0; yv < 4; ++yv) {
+                const int j = 4 * tj + yv;
+                if (j > i) continue;
+                float2 g = acc[x][yv];
+                if (i == j) g.y = 0.f;
+                GV[pk(i, j)] = g;
+                if (with_c) {
+                    float2 c = make_float2(0.f, 0.f);
+                    if (i == j) c.x = (i < n) ? hs[i] : c1z;
+                    else if (i == n) c = cconj(phis[j]);
+                    const float rx = g.x - c.x, ry = g.y - c.y;
+                    rsq += (i == j ? 1.f : 2.f) * (rx * rx + ry * ry);
+                }
+            }
+        }
+    }
+    return rsq;
+}
+
 // =====================================================================================
 // k_tail: U = Q_H Z, l' = f(l), G = U diag(l') U^H (lower triangle), r = ||G - C||_F.
 // Thread mapping for the back-transformation: (column pair cp = tid>>3, row split s = tid&7),
@@ -1224,6 +1291,7 @@ struct TailArgs {
     float2* U_out;          // optional [B][d][d] row-major eigenvectors (debug taps), may be null
     float* lamp_out;        // optional [B][d]
     int B, n, d, ldu, with_c;  // with_c=0: plain f(A) for the debug entry (no residual)
+    const int* skip;
 };
 __host__ __device__ inline size_t tail_smem_bytes(int d, int ldu) {
     const size_t nv = (size_t)d * (d - 1) / 2;
@@ -1244,6 +1312,7 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     float* red = hs + 128;
     const int tid = threadIdx.x;
     const int sig = blockIdx.x;
+    if (a.skip && a.skip[sig]) return;
     const int npk = d * (d + 1) / 2;
     float2* GV = a.GV + (size_t)sig * npk;
     const float* __restrict__ P = a.Pk;
@@ -1337,63 +1406,8 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     }
     __syncthreads();
 
-    // ---- phase D: G = U diag(l') U^H on 4x4 register tiles of the lower triangle
-    const int nt1 = (d + 3) / 4;
-    const int ntiles = nt1 * (nt1 + 1) / 2;
-    const float c1z = P ? P[P_C1Z] : 0.f;
-    float rsq = 0.f;
-    for (int t = tid; t < ntiles; t += NT) {
-        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        while (ti * (ti + 1) / 2 > t) --ti;
-        const int tj = t - ti * (ti + 1) / 2;
-        float2 acc[4][4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int yv = 0; yv < 4; ++yv) acc[x][yv] = make_float2(0.f, 0.f);
-        const float4* Ua = reinterpret_cast<const float4*>(U + 4 * ti);
-        const float4* Ub = reinterpret_cast<const float4*>(U + 4 * tj);
-        const int ld4 = ldu / 2;   // float4 stride per column
-        for (int k = 0; k < d; ++k) {
-            const float lp = lamp[k];
-            const float4 a01 = Ua[(size_t)k * ld4], a23 = Ua[(size_t)k * ld4 + 1];
-            const float4 b01 = Ub[(size_t)k * ld4], b23 = Ub[(size_t)k * ld4 + 1];
-            const float2 av[4] = {make_float2(lp * a01.x, lp * a01.y), make_float2(lp * a01.z, lp * a01.w),
-                                  make_float2(lp * a23.x, lp * a23.y), make_float2(lp * a23.z, lp * a23.w)};
-            const float2 bv[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y),
-                                  make_float2(b23.z, b23.w)};
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int yv = 0; yv < 4; ++yv) {
-                    acc[x][yv].x = fmaf(av[x].x, bv[yv].x, acc[x][yv].x);
-                    acc[x][yv].x = fmaf(av[x].y, bv[yv].y, acc[x][yv].x);
-                    acc[x][yv].y = fmaf(av[x].y, bv[yv].x, acc[x][yv].y);
-                    acc[x][yv].y = fmaf(-av[x].x, bv[yv].y, acc[x][yv].y);
-                }
-        }
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const int i = 4 * ti + x;
-            if (i >= d) continue;
-#pragma unroll
-            for (int yv = 0; yv < 4; ++yv) {
-                const int j = 4 * tj + yv;
-                if (j > i) continue;
-                float2 g = acc[x][yv];
-                if (i == j) g.y = 0.f;
-                GV[pk(i, j)] = g;
-                if (a.with_c > 0) {
-                    float2 c = make_float2(0.f, 0.f);
-                    if (i == j) c.x = (i < n) ? hs[i] : c1z;
-                    else if (i == n) c = cconj(phis[j]);
-                    const float rx = g.x - c.x, ry = g.y - c.y;
-                    rsq += (i == j ? 1.f : 2.f) * (rx * rx + ry * ry);
-                }
-            }
-        }
-    }
+    // ---- phase D: G = U diag(l') U^H (lower triangle) and the residual norm
+    const float rsq = rebuild_lower<NT>(U, ldu, lamp, d, n, GV, hs, phis, P ? P[P_C1Z] : 0.f, a.with_c > 0);
     if (a.with_c > 0) {
         float v[1] = {rsq};
         block_sum<1>(v, red);

@@ -93,6 +93,15 @@ int admmnet_eigh_workspace_bytes(int B, int d, int rcap, size_t* bytes);
 int admmnet_eigh_batched(const void* A, int B, int d, float* evals, void* evecs, void* fn_out, const float* params,
                          void* ws, size_t ws_bytes, int rcap, void* stream, int* status_dev);
 
+/* Unit tap of the layer-0 shortcut: eigen-decomposition of the arrowhead matrices
+ * [[diag(h), phi],[phi^H, c0]] that admm_net.py:286-303 hands to eigh when G = Z = 0.
+ *   h float32 [B][n], phi complex64 [B][n], c0 float32 [B]
+ *   evals float32 [B][n+1] ascending; evecs complex64 [B][n+1][n+1] row-major (may be NULL)
+ *   handled int [B]: 0 = declined (poles closer than rounding or a vanishing |phi_i|; admmnet_forward sends
+ *   such signals through the general eigen-solver), outputs then undefined                                */
+int admmnet_arrow_eigh(const float* h, const void* phi, const float* c0, int B, int n, float* evals, void* evecs,
+                       int* handled, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Classical ADMM  (replaces admm.py:6-114 admm_for_us; see SURVEY.md App. A.3 for why the solver
  * is the linear recursion phi_k = M^-1 (y/b + rho phi_{k-1}) for every reachable input)

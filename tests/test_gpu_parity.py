@@ -87,6 +87,83 @@ def test_eigh_structured_cases(pkg):
     assert (ev.sort(dim=1)[0] - w).abs().amax() < 2e-5 * 101
 
 
+def _arrow_eigh(h, phi, c0):
+    import ctypes as C
+    from admmnet_b200 import _capi
+    L = _capi.lib()
+    B, n = h.shape
+    hd, pd, cd = h.cuda().contiguous(), phi.cuda().contiguous(), c0.cuda().contiguous()
+    ev = torch.zeros(B, n + 1, dtype=torch.float32, device="cuda")
+    U = torch.zeros(B, n + 1, n + 1, dtype=torch.complex64, device="cuda")
+    ok = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    _capi.check(L.admmnet_arrow_eigh(hd.data_ptr(), pd.data_ptr(), cd.data_ptr(), B, n, ev.data_ptr(), U.data_ptr(),
+                                     ok.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return ev.cpu(), U.cpu(), ok.cpu()
+
+
+def _arrow_dense(h, phi, c0):
+    B, n = h.shape
+    A = torch.zeros(B, n + 1, n + 1, dtype=torch.complex64)
+    A[:, :n, :n] = torch.diag_embed(h).to(torch.complex64)
+    A[:, :n, n] = phi
+    A[:, n, :n] = phi.conj()
+    A[:, n, n] = c0.to(torch.complex64)
+    return A
+
+
+@pytest.mark.parametrize("n", [2, 5, 33, 100, 127])
+def test_arrowhead_shortcut_eigenpairs(pkg, n):
+    """Layer-0 shortcut (App. A.2): eigenpairs of [[diag(h), phi],[phi^H, c0]] against torch fp64 eigh."""
+    torch.manual_seed(n)
+    B = 8
+    h = torch.randn(B, n) * 0.1
+    phi = torch.randn(B, n, dtype=torch.complex64)
+    c0 = torch.full((B,), 1.8)
+    h[1] = torch.sort(torch.rand(n))[0] * 1e-3                       # tight cluster of poles
+    h[2, : n // 2] = h[2, n // 2: 2 * (n // 2)] + 3e-7             # pairs of nearly equal poles
+    phi[3] *= 1e-3                                                  # weak coupling: roots hug the poles
+    phi[4, ::2] *= 1e-4                                             # mixed magnitudes
+    c0[5] = -7.0                                                    # corner element below every pole
+    h[6] *= 50.0
+    ev, U, ok = _arrow_eigh(h, phi, c0)
+    assert ok.tolist() == [1] * B
+    A = _arrow_dense(h, phi, c0)
+    scale = torch.linalg.matrix_norm(A, ord=2).view(B, 1, 1)
+    assert ((A @ U - U * ev.unsqueeze(1).to(torch.complex64)).abs() / scale).amax() < 4e-6
+    assert (U.transpose(1, 2).conj() @ U - torch.eye(n + 1)).abs().amax() < 4e-6
+    w = torch.linalg.eigvalsh(A.to(torch.complex128)).float()
+    assert ((ev - w).abs() / scale.view(B, 1)).amax() < 1e-6          # ascending order, like torch
+
+
+def test_arrowhead_shortcut_declines_degenerate_input(pkg):
+    n = 100
+    torch.manual_seed(0)
+    h = torch.randn(4, n) * 0.1
+    phi = torch.randn(4, n, dtype=torch.complex64)
+    c0 = torch.full((4,), 1.8)
+    h[0, 7] = h[0, 3]                    # repeated pole
+    phi[1, 11] = 0                       # decoupled row
+    h[2, 5] = float("nan")
+    ev, U, ok = _arrow_eigh(h, phi, c0)
+    assert ok.tolist() == [0, 0, 0, 1]
+
+
+def test_forward_general_path_at_layer0_when_shortcut_declines(pkg):
+    """A signal whose y has a zero entry makes phi_i = 0 at layer 0: k_arrow declines, the dense solver takes it, and
+    the result still matches the oracle; the other signals of the batch go through the shortcut."""
+    from oracle import net_oracle
+    z, sd = load_net_case("pert_k5")
+    K = int(z["K"])
+    net = pkg.PhiEstADMMNet(10, 10, 3, K).eval()
+    net.load_state_dict(sd)
+    y, b, s = (torch.from_numpy(z[k]).clone() for k in ("y", "b", "sigma"))
+    y[2, 17] = 0
+    got = net(y, b, s).numpy()
+    ref = net_oracle.forward(sd, y, b, s, 10, 10, K).numpy()
+    assert rel_err(got, ref).max() < 1e-4
+
+
 def test_hermitian_function_matches_oracle(pkg):
     """f(A) = U f(L) U^H with the learned eigenvalue map: basis-invariant, compared with torch fp64."""
     from admmnet_b200.params import pack_state_dict
