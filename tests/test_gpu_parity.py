@@ -10,6 +10,7 @@ import torch
 from tests.helpers import GOLDEN, load_net_case, parse_opts, rel_err
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # BASELINE.json north_star: 1e-4 relative on the recovered phi (max-norm per signal)
 PHI_TOL = 1e-4
@@ -444,3 +445,32 @@ def test_admmnet_full_module_matches_reference_golden(pkg):
     # ragged batch (not a multiple of the 8 signals a CTA takes)
     t3, _, _ = net.head_device(torch.from_numpy(z["phi"][:5]).cuda())
     np.testing.assert_allclose(t3.cpu().numpy(), z["tau"][:5], atol=2e-6, rtol=1e-5)
+
+
+def test_layer0_shortcut_and_general_path_agree(pkg, tmp_path):
+    """The same forward with the arrowhead shortcut (default) and with ADMMNET_ARROW=0 (dense eigen-solver at layer 0
+    too; the switch is read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    z, sd = load_net_case("pert_k10")
+    net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
+    net.load_state_dict(sd)
+    y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
+    with torch.no_grad():
+        phi = net(y, b, s).numpy()
+    out = str(tmp_path / "phi_general.npy")
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import admmnet_b200 as pkg\n"
+        "from tests.helpers import load_net_case\n"
+        "z, sd = load_net_case('pert_k10')\n"
+        "net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval(); net.load_state_dict(sd)\n"
+        "y, b, s = (torch.from_numpy(z[k]) for k in ('y', 'b', 'sigma'))\n"
+        "with torch.no_grad():\n"
+        f"    np.save({out!r}, net(y, b, s).numpy())\n")
+    env = dict(os.environ, ADMMNET_ARROW="0")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    phi_general = np.load(out)
+    assert rel_err(phi, phi_general).max() < 3e-5
+    assert rel_err(phi_general, z["phi_batch"]).max() < PHI_TOL
