@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(AR_NT, 2) k_arrow(ArrowArgs a) {
         return;
     }
     // ---- G = U f(L) U^H, r = ||G - C||_F
-    const float rsq = rebuild_lower<AR_NT>(U, ldu, lamp, d, n, GV, hs, phis, P[P_C1Z], true);
+    const float rsq = rebuild_lower<AR_NT, false>(U, ldu, lamp, d, n, GV, hs, phis, P[P_C1Z], true);
     float v[1] = {rsq};
     block_sum<1>(v, red);
     if (tid == 0) a.r_out[sig] = sqrtf(v[0]);

@@ -300,12 +300,13 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c; t.skip = skip;
         const size_t sm = tail_smem_bytes(d, t.ldu);
         prof::Scope pscope(prof::TAIL, st);
+        // (a 16-lane row split, k_tail<7, 832, 16>, doubles the warps per SM but measured 25 % slower)
         if (d <= 104) {
-            CK(cudaFuncSetAttribute(k_tail<13, 416>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_tail<13, 416><<<B, 416, sm, st>>>(t);
+            CK(cudaFuncSetAttribute(k_tail<13, 416, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_tail<13, 416, 8><<<B, 416, sm, st>>>(t);
         } else {
-            CK(cudaFuncSetAttribute(k_tail<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_tail<16, 512><<<B, 512, sm, st>>>(t);
+            CK(cudaFuncSetAttribute(k_tail<16, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_tail<16, 512, 8><<<B, 512, sm, st>>>(t);
         }
         CK(cudaGetLastError());
     }

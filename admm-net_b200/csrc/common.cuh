@@ -100,6 +100,32 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return warp_max(x);
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: two fp32 lanes per issue slot, same rounding as two FFMA).
+// ptxas folds pk2(s, s) into a scalar-broadcast operand and lane swaps / sign changes into operand modifiers, so a
+// complex multiply-add costs two issue slots instead of four.  Lane 0 = .x ("lo"), lane 1 = .y ("hi").
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
+
 // packed lower-triangular (row-major) index, j <= i
 __host__ __device__ __forceinline__ int pk(int i, int j) { return (i * (i + 1)) / 2 + j; }
 // Householder-vector store: column k holds rows k+1..d-1 (v[k+1] == 1 stored explicitly), columns concatenated

@@ -751,11 +751,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __device__ __forceinline__ void rot4(float4& out, float4& cy, const float4 zi, const float2 e) {
-    // z[i+1] = s*z[i] + c*f ;  z[i] = c*z[i] - s*f   (f = carry), four rows at once
-    out.x = fmaf(e.y, zi.x, e.x * cy.x); cy.x = fmaf(e.x, zi.x, -e.y * cy.x);
-    out.y = fmaf(e.y, zi.y, e.x * cy.y); cy.y = fmaf(e.x, zi.y, -e.y * cy.y);
-    out.z = fmaf(e.y, zi.z, e.x * cy.z); cy.z = fmaf(e.x, zi.z, -e.y * cy.z);
-    out.w = fmaf(e.y, zi.w, e.x * cy.w); cy.w = fmaf(e.x, zi.w, -e.y * cy.w);
+    // z[i+1] = s*z[i] + c*f ;  z[i] = c*z[i] - s*f   (f = carry), four rows at once as two packed pairs
+    // (FMUL2 + FFMA2: 8 issue slots instead of 16, same rounding)
+    const f32x2 c2 = bc2(e.x), s2 = bc2(e.y), ns2 = bc2(-e.y);
+    const f32x2 z01 = pk2(zi.x, zi.y), z23 = pk2(zi.z, zi.w);
+    const f32x2 f01 = pk2(cy.x, cy.y), f23 = pk2(cy.z, cy.w);
+    const float2 o01 = upk2(fma2(s2, z01, mul2(c2, f01))), o23 = upk2(fma2(s2, z23, mul2(c2, f23)));
+    const float2 n01 = upk2(fma2(c2, z01, mul2(ns2, f01))), n23 = upk2(fma2(c2, z23, mul2(ns2, f23)));
+    out = make_float4(o01.x, o01.y, o23.x, o23.y);
+    cy = make_float4(n01.x, n01.y, n23.x, n23.y);
 }
 
 // One WARP per signal (CTA = 1 warp, ~46 KB of shared memory -> 4-5 CTAs per SM).  Z is kept TRANSPOSED in
@@ -1211,7 +1215,7 @@ __global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
 
 // G = U diag(l') U^H on 4x4 register tiles of the lower triangle, written packed to GV; returns this thread's share
 // of ||G - C||_F^2 (C = [[diag(h), phi],[phi^H, c1z]]) when with_c.  U is column-major [k][ldu] in shared memory.
-template <int NT>
+template <int NT, bool PACKED>
 __device__ __forceinline__ float rebuild_lower(const float2* __restrict__ U, int ldu, const float* __restrict__ lamp,
                                                int d, int n, float2* __restrict__ GV, const float* __restrict__ hs,
                                                const float2* __restrict__ phis, float c1z, bool with_c) {
@@ -1224,31 +1228,65 @@ __device__ __forceinline__ float rebuild_lower(const float2* __restrict__ U, int
         while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
         while (ti * (ti + 1) / 2 > t) --ti;
         const int tj = t - ti * (ti + 1) / 2;
-        float2 acc[4][4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int yv = 0; yv < 4; ++yv) acc[x][yv] = make_float2(0.f, 0.f);
         const float4* Ua = reinterpret_cast<const float4*>(U + 4 * ti);
         const float4* Ub = reinterpret_cast<const float4*>(U + 4 * tj);
         const int ld4 = ldu / 2;   // float4 stride per column
-        for (int k = 0; k < d; ++k) {
-            const float lp = lamp[k];
-            const float4 a01 = Ua[(size_t)k * ld4], a23 = Ua[(size_t)k * ld4 + 1];
-            const float4 b01 = Ub[(size_t)k * ld4], b23 = Ub[(size_t)k * ld4 + 1];
-            const float2 av[4] = {make_float2(lp * a01.x, lp * a01.y), make_float2(lp * a01.z, lp * a01.w),
-                                  make_float2(lp * a23.x, lp * a23.y), make_float2(lp * a23.z, lp * a23.w)};
-            const float2 bv[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y),
-                                  make_float2(b23.z, b23.w)};
+        float2 acc[4][4];
+        if constexpr (PACKED) {
+            // acc[x][y] = sum_k (l' u_x) conj(u_y) with packed FMAs and no operand shuffling: with a = l' u_x as the
+            // (re, im) pair,  P += b.re * a  and  Q += b.im * a  (b = u_y as broadcast scalars), and at the end
+            // acc = (P.re + Q.im, P.im - Q.re).
+            f32x2 Pp[4][4], Qp[4][4];
+    #pragma unroll
+            for (int x = 0; x < 4; ++x)
+    #pragma unroll
+                for (int yv = 0; yv < 4; ++yv) { Pp[x][yv] = pk2(0.f, 0.f); Qp[x][yv] = pk2(0.f, 0.f); }
+            for (int k = 0; k < d; ++k) {
+                const f32x2 lp = bc2(lamp[k]);
+                const float4 a01 = Ua[(size_t)k * ld4], a23 = Ua[(size_t)k * ld4 + 1];
+                const float4 b01 = Ub[(size_t)k * ld4], b23 = Ub[(size_t)k * ld4 + 1];
+                const f32x2 av[4] = {mul2(lp, pk2(a01.x, a01.y)), mul2(lp, pk2(a01.z, a01.w)), mul2(lp, pk2(a23.x, a23.y)),
+                                     mul2(lp, pk2(a23.z, a23.w))};
+                const float bre[4] = {b01.x, b01.z, b23.x, b23.z}, bim[4] = {b01.y, b01.w, b23.y, b23.w};
+    #pragma unroll
+                for (int x = 0; x < 4; ++x)
+    #pragma unroll
+                    for (int yv = 0; yv < 4; ++yv) {
+                        Pp[x][yv] = fma2(bc2(bre[yv]), av[x], Pp[x][yv]);
+                        Qp[x][yv] = fma2(bc2(bim[yv]), av[x], Qp[x][yv]);
+                    }
+            }
+    #pragma unroll
+            for (int x = 0; x < 4; ++x)
+    #pragma unroll
+                for (int yv = 0; yv < 4; ++yv) {
+                    const float2 pp = upk2(Pp[x][yv]), qq = upk2(Qp[x][yv]);
+                    acc[x][yv] = make_float2(pp.x + qq.y, pp.y - qq.x);
+                }
+        } else {
+            // scalar form (k_arrow: its two-CTA register budget has no room for the second accumulator set)
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                for (int yv = 0; yv < 4; ++yv) {
-                    acc[x][yv].x = fmaf(av[x].x, bv[yv].x, acc[x][yv].x);
-                    acc[x][yv].x = fmaf(av[x].y, bv[yv].y, acc[x][yv].x);
-                    acc[x][yv].y = fmaf(av[x].y, bv[yv].x, acc[x][yv].y);
-                    acc[x][yv].y = fmaf(-av[x].x, bv[yv].y, acc[x][yv].y);
-                }
+                for (int yv = 0; yv < 4; ++yv) acc[x][yv] = make_float2(0.f, 0.f);
+            for (int k = 0; k < d; ++k) {
+                const float lp = lamp[k];
+                const float4 a01 = Ua[(size_t)k * ld4], a23 = Ua[(size_t)k * ld4 + 1];
+                const float4 b01 = Ub[(size_t)k * ld4], b23 = Ub[(size_t)k * ld4 + 1];
+                const float2 av[4] = {make_float2(lp * a01.x, lp * a01.y), make_float2(lp * a01.z, lp * a01.w),
+                                      make_float2(lp * a23.x, lp * a23.y), make_float2(lp * a23.z, lp * a23.w)};
+                const float2 bv[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y),
+                                      make_float2(b23.z, b23.w)};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int yv = 0; yv < 4; ++yv) {
+                        acc[x][yv].x = fmaf(av[x].x, bv[yv].x, acc[x][yv].x);
+                        acc[x][yv].x = fmaf(av[x].y, bv[yv].y, acc[x][yv].x);
+                        acc[x][yv].y = fmaf(av[x].y, bv[yv].x, acc[x][yv].y);
+                        acc[x][yv].y = fmaf(-av[x].x, bv[yv].y, acc[x][yv].y);
+                    }
+            }
         }
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -1298,7 +1336,7 @@ __host__ __device__ inline size_t tail_smem_bytes(int d, int ldu) {
     return ((size_t)d * ldu + nv + 2 + 128 /*tau*/ + 128 /*phi*/) * sizeof(float2) + (128 + 128 + 96) * sizeof(float);
 }
 
-template <int NR, int NT>
+template <int NR, int NT, int RL>
 __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, d = a.d, ldu = a.ldu;
@@ -1338,14 +1376,17 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     __syncthreads();
 
     // ---- phase B: back-transformation in registers
-    const int s8 = tid & 7, cp = tid >> 3;
+    const int s8 = tid & (RL - 1), cp = tid / RL;        // RL lanes share a column pair, rows s8 + RL*j
     const int c0 = 2 * cp, c1 = 2 * cp + 1;
-    float2 M0[NR], M1[NR];
+    // The two columns of a thread are kept as packed pairs across the columns: Mx[j] = (Re M0[j], Re M1[j]),
+    // My[j] = (Im M0[j], Im M1[j]); with the reflector entry as a broadcast operand every complex multiply-add of the
+    // pair of columns is two FFMA2 (same operation order and rounding as the scalar form).
+    f32x2 Mx[NR], My[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
-        const int r = s8 + 8 * j;
-        M0[j] = make_float2((r < d && c0 < d) ? Zs[c0 * d + r] : 0.f, 0.f);
-        M1[j] = make_float2((r < d && c1 < d) ? Zs[c1 * d + r] : 0.f, 0.f);
+        const int r = s8 + RL * j;
+        Mx[j] = pk2((r < d && c0 < d) ? Zs[c0 * d + r] : 0.f, (r < d && c1 < d) ? Zs[c1 * d + r] : 0.f);
+        My[j] = pk2(0.f, 0.f);
     }
     __syncthreads();   // Z staging area is dead from here on (becomes U)
     // Reflector k touches rows r > k.  Rows are held as r = s8 + 8j, so for the 8 reflectors with
@@ -1353,47 +1394,52 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     // unconditionally (compile-time bounds after unrolling jm -> no per-slot branches in the hot loop).
 #pragma unroll
     for (int jm = NR - 1; jm >= 0; --jm) {
-        const int khi = min(8 * jm + 6, d - 2), klo = max(8 * jm - 1, 0);
+        const int khi = min(RL * jm + RL - 2, d - 2), klo = max(RL * jm - 1, 0);
         for (int k = khi; k >= klo; --k) {
             const float2 tk = taus[k];
             if (tk.x == 0.f && tk.y == 0.f) continue;
             const int vbase = voff(k, d) - (k + 1);           // Vs[vbase + r] valid for r >= k+1
             float2 vv[NR];
-            float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
+            f32x2 Dx = pk2(0.f, 0.f), Dy = pk2(0.f, 0.f);     // conj(v) . M for both columns
 #pragma unroll
             for (int j = jm; j < NR; ++j) {
-                const int r = s8 + 8 * j;
+                const int r = s8 + RL * j;
                 const bool on = (j == jm ? r > k : true) && (r < d);
                 float2 v = make_float2(0.f, 0.f);
                 if (on) v = Vs[vbase + r];
                 vv[j] = v;
-                d0.x = fmaf(v.x, M0[j].x, d0.x); d0.x = fmaf(v.y, M0[j].y, d0.x);
-                d0.y = fmaf(v.x, M0[j].y, d0.y); d0.y = fmaf(-v.y, M0[j].x, d0.y);
-                d1.x = fmaf(v.x, M1[j].x, d1.x); d1.x = fmaf(v.y, M1[j].y, d1.x);
-                d1.y = fmaf(v.x, M1[j].y, d1.y); d1.y = fmaf(-v.y, M1[j].x, d1.y);
+                Dx = fma2(bc2(v.x), Mx[j], Dx); Dx = fma2(bc2(v.y), My[j], Dx);
+                Dy = fma2(bc2(v.x), My[j], Dy); Dy = fma2(bc2(-v.y), Mx[j], Dy);
             }
+            float2 dx = upk2(Dx), dy = upk2(Dy);              // dx = (d0.x, d1.x), dy = (d0.y, d1.y)
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                d0.x += __shfl_xor_sync(0xffffffffu, d0.x, o);
-                d0.y += __shfl_xor_sync(0xffffffffu, d0.y, o);
-                d1.x += __shfl_xor_sync(0xffffffffu, d1.x, o);
-                d1.y += __shfl_xor_sync(0xffffffffu, d1.y, o);
+            for (int o = 1; o < RL; o <<= 1) {
+                dx.x += __shfl_xor_sync(0xffffffffu, dx.x, o);
+                dy.x += __shfl_xor_sync(0xffffffffu, dy.x, o);
+                dx.y += __shfl_xor_sync(0xffffffffu, dx.y, o);
+                dy.y += __shfl_xor_sync(0xffffffffu, dy.y, o);
             }
-            const float2 t0 = cmul(tk, d0), t1 = cmul(tk, d1);
+            const float2 t0 = cmul(tk, make_float2(dx.x, dy.x)), t1 = cmul(tk, make_float2(dx.y, dy.y));
+            const f32x2 nTx = pk2(-t0.x, -t1.x), Ty = pk2(t0.y, t1.y), nTy = pk2(-t0.y, -t1.y);
 #pragma unroll
             for (int j = jm; j < NR; ++j) {
                 const float2 v = vv[j];
-                M0[j].x = fmaf(-t0.x, v.x, M0[j].x); M0[j].x = fmaf(t0.y, v.y, M0[j].x);
-                M0[j].y = fmaf(-t0.x, v.y, M0[j].y); M0[j].y = fmaf(-t0.y, v.x, M0[j].y);
-                M1[j].x = fmaf(-t1.x, v.x, M1[j].x); M1[j].x = fmaf(t1.y, v.y, M1[j].x);
-                M1[j].y = fmaf(-t1.x, v.y, M1[j].y); M1[j].y = fmaf(-t1.y, v.x, M1[j].y);
+                Mx[j] = fma2(bc2(v.x), nTx, Mx[j]); Mx[j] = fma2(bc2(v.y), Ty, Mx[j]);
+                My[j] = fma2(bc2(v.y), nTx, My[j]); My[j] = fma2(bc2(v.x), nTy, My[j]);
             }
         }
+    }
+    float2 M0[NR], M1[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const float2 mx = upk2(Mx[j]), my = upk2(My[j]);
+        M0[j] = make_float2(mx.x, my.x);
+        M1[j] = make_float2(mx.y, my.y);
     }
     // ---- phase C: U to shared memory (column-major, zero padded rows) and optional global tap
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
-        const int r = s8 + 8 * j;
+        const int r = s8 + RL * j;
         if (r < ldu) {
             if (c0 < d) U[(size_t)c0 * ldu + r] = r < d ? M0[j] : make_float2(0.f, 0.f);
             if (c1 < d) U[(size_t)c1 * ldu + r] = r < d ? M1[j] : make_float2(0.f, 0.f);
@@ -1407,7 +1453,7 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     __syncthreads();
 
     // ---- phase D: G = U diag(l') U^H (lower triangle) and the residual norm
-    const float rsq = rebuild_lower<NT>(U, ldu, lamp, d, n, GV, hs, phis, P ? P[P_C1Z] : 0.f, a.with_c > 0);
+    const float rsq = rebuild_lower<NT, true>(U, ldu, lamp, d, n, GV, hs, phis, P ? P[P_C1Z] : 0.f, a.with_c > 0);
     if (a.with_c > 0) {
         float v[1] = {rsq};
         block_sum<1>(v, red);
