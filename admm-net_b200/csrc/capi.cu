@@ -298,8 +298,20 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         t.Zr = zfinal; t.GV = w.GV; t.tau = w.tau; t.lam = w.lam; t.phi_cur = w.phi_cur; t.h_cur = w.h_cur;
         t.Pk = Pk; t.r_out = w.r; t.U_out = U_out; t.lamp_out = lamp_out;
         t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c; t.skip = skip;
-        const size_t sm = tail_smem_bytes(d, t.ldu);
         prof::Scope pscope(prof::TAIL, st);
+        static const bool persistent = !(getenv("ADMMNET_TAILP") && atoi(getenv("ADMMNET_TAILP")) == 0);
+        const size_t smp = tailp_smem_bytes(d, t.ldu);
+        if (persistent && d <= 104 && with_c > 0 && !U_out && !lamp_out && !skip && smp <= 227 * 1024) {
+            // production form: persistent CTAs (one per SM) with the next signal's operands prefetched
+            int dev = 0, nsm = 0;
+            CK(cudaGetDevice(&dev));
+            CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+            CK(cudaFuncSetAttribute(k_tail_p<13, 416, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp));
+            k_tail_p<13, 416, 8><<<B < nsm ? B : nsm, 416, smp, st>>>(t);
+            CK(cudaGetLastError());
+            return 0;
+        }
+        const size_t sm = tail_smem_bytes(d, t.ldu);
         // (a 16-lane row split, k_tail<7, 832, 16>, doubles the warps per SM but measured 25 % slower)
         if (d <= 104) {
             CK(cudaFuncSetAttribute(k_tail<13, 416, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

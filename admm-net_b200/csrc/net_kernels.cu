@@ -1461,6 +1461,147 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     }
 }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+
+// =====================================================================================
+// k_tail_p: the production form of k_tail (layers >= 1 of admmnet_forward).  Persistent: one CTA per SM walks the
+// signals sig = blockIdx.x, blockIdx.x + gridDim.x, ...; while a signal is being back-transformed and rebuilt, the
+// NEXT signal's Z^T, reflectors, tau, eigenvalues, phi and h stream into a second set of shared-memory buffers with
+// cp.async, so the HBM/L2 latency of the staging (11 % of k_tail's time at one CTA per SM) is hidden.
+// Shared memory: U [d][ldu] c64 | V[2] reflectors | Zn (next Z^T, consumed into registers at the top of an
+// iteration and refilled right away) | small per-signal vectors [2]  = 205 KB at d = 101.
+// =====================================================================================
+__host__ __device__ inline size_t tailp_smem_bytes(int d, int ldu) {
+    const size_t nv2 = ((size_t)d * (d - 1) / 2 + 1) & ~(size_t)1;
+    const size_t zf = ((size_t)d * d + 3) & ~(size_t)3;
+    return ((size_t)d * ldu + 2 * nv2 + 2 * 128 /*tau*/ + 2 * 128 /*phi*/) * sizeof(float2) +
+           (zf + 2 * 128 /*lam*/ + 2 * 128 /*h*/ + 128 /*lamp*/ + 96) * sizeof(float);
+}
+template <int NR, int NT, int RL>
+__global__ void __launch_bounds__(NT, 1) k_tail_p(TailArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, d = a.d, ldu = a.ldu;
+    const int nv = d * (d - 1) / 2;
+    const int nv2 = (nv + 1) & ~1;
+    const int zf = (d * d + 3) & ~3;
+    float2* U = reinterpret_cast<float2*>(smem_raw);          // [d][ldu] column-major
+    float2* Vb = U + (size_t)d * ldu;                         // [2][nv2] reflectors
+    float2* taub = Vb + 2 * (size_t)nv2;                      // [2][128]
+    float2* phib = taub + 2 * 128;                            // [2][128]
+    float* Zn = reinterpret_cast<float*>(phib + 2 * 128);     // [d*d] Z^T of the coming signal
+    float* lamb = Zn + zf;                                    // [2][128] eigenvalues
+    float* hb = lamb + 2 * 128;                               // [2][128]
+    float* lamp = hb + 2 * 128;                               // [128] mapped eigenvalues
+    float* red = lamp + 128;
+    const int tid = threadIdx.x;
+    const int npk = d * (d + 1) / 2;
+    const float* __restrict__ P = a.Pk;
+    const float c1z = P[P_C1Z];
+
+    auto prefetch = [&](int sig, int buf) {                   // everything signal `sig` needs, one cp.async group
+        const float2* gv = a.GV + (size_t)sig * npk;
+        float2* vd = Vb + (size_t)buf * nv2;
+        for (int idx = tid; idx < nv; idx += NT) cp_async8(vd + idx, gv + idx);
+        const float* zg = a.Zr + (size_t)sig * d * d;
+        for (int idx = tid; idx < d * d; idx += NT) cp_async4(Zn + idx, zg + idx);
+        for (int i = tid; i < d; i += NT) {
+            cp_async8(taub + buf * 128 + i, a.tau + (size_t)sig * d + i);
+            cp_async4(lamb + buf * 128 + i, a.lam + (size_t)sig * d + i);
+        }
+        for (int j = tid; j < n; j += NT) {
+            cp_async8(phib + buf * 128 + j, a.phi_cur + (size_t)sig * n + j);
+            cp_async4(hb + buf * 128 + j, a.h_cur + (size_t)sig * n + j);
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    if ((int)blockIdx.x < a.B) prefetch(blockIdx.x, 0);
+    for (int sig = blockIdx.x; sig < a.B; sig += gridDim.x, buf ^= 1) {
+        float2* GV = a.GV + (size_t)sig * npk;
+        const float2* Vs = Vb + (size_t)buf * nv2;
+        const float2* taus = taub + buf * 128;
+        const float2* phis = phib + buf * 128;
+        const float* hs = hb + buf * 128;
+        cp_async_wait<0>();
+        __syncthreads();              // this signal's data has landed; the previous signal's rebuild is finished
+        // ---- Z into registers (packed pairs across the thread's two columns)
+        const int s8 = tid & (RL - 1), cp = tid / RL;
+        const int c0 = 2 * cp, c1 = 2 * cp + 1;
+        f32x2 Mx[NR], My[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const int r = s8 + RL * j;
+            Mx[j] = pk2((r < d && c0 < d) ? Zn[c0 * d + r] : 0.f, (r < d && c1 < d) ? Zn[c1 * d + r] : 0.f);
+            My[j] = pk2(0.f, 0.f);
+        }
+        if (tid < d) lamp[tid] = eig_map(P, lamb[buf * 128 + tid]);
+        __syncthreads();              // Zn is free again
+        if (sig + (int)gridDim.x < a.B) prefetch(sig + gridDim.x, buf ^ 1);
+        // ---- back-transformation (see k_tail)
+#pragma unroll
+        for (int jm = NR - 1; jm >= 0; --jm) {
+            const int khi = min(RL * jm + RL - 2, d - 2), klo = max(RL * jm - 1, 0);
+            for (int k = khi; k >= klo; --k) {
+                const float2 tk = taus[k];
+                if (tk.x == 0.f && tk.y == 0.f) continue;
+                const int vbase = voff(k, d) - (k + 1);
+                float2 vv[NR];
+                f32x2 Dx = pk2(0.f, 0.f), Dy = pk2(0.f, 0.f);
+#pragma unroll
+                for (int j = jm; j < NR; ++j) {
+                    const int r = s8 + RL * j;
+                    const bool on = (j == jm ? r > k : true) && (r < d);
+                    float2 v = make_float2(0.f, 0.f);
+                    if (on) v = Vs[vbase + r];
+                    vv[j] = v;
+                    Dx = fma2(bc2(v.x), Mx[j], Dx); Dx = fma2(bc2(v.y), My[j], Dx);
+                    Dy = fma2(bc2(v.x), My[j], Dy); Dy = fma2(bc2(-v.y), Mx[j], Dy);
+                }
+                float2 dx = upk2(Dx), dy = upk2(Dy);
+#pragma unroll
+                for (int o = 1; o < RL; o <<= 1) {
+                    dx.x += __shfl_xor_sync(0xffffffffu, dx.x, o);
+                    dy.x += __shfl_xor_sync(0xffffffffu, dy.x, o);
+                    dx.y += __shfl_xor_sync(0xffffffffu, dx.y, o);
+                    dy.y += __shfl_xor_sync(0xffffffffu, dy.y, o);
+                }
+                const float2 t0 = cmul(tk, make_float2(dx.x, dy.x)), t1 = cmul(tk, make_float2(dx.y, dy.y));
+                const f32x2 nTx = pk2(-t0.x, -t1.x), Ty = pk2(t0.y, t1.y), nTy = pk2(-t0.y, -t1.y);
+#pragma unroll
+                for (int j = jm; j < NR; ++j) {
+                    const float2 v = vv[j];
+                    Mx[j] = fma2(bc2(v.x), nTx, Mx[j]); Mx[j] = fma2(bc2(v.y), Ty, Mx[j]);
+                    My[j] = fma2(bc2(v.y), nTx, My[j]); My[j] = fma2(bc2(v.x), nTy, My[j]);
+                }
+            }
+        }
+        // ---- U to shared memory (column-major, zero padded rows)
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const int r = s8 + RL * j;
+            const float2 mx = upk2(Mx[j]), my = upk2(My[j]);
+            if (r < ldu) {
+                if (c0 < d) U[(size_t)c0 * ldu + r] = r < d ? make_float2(mx.x, my.x) : make_float2(0.f, 0.f);
+                if (c1 < d) U[(size_t)c1 * ldu + r] = r < d ? make_float2(mx.y, my.y) : make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- G = U diag(l') U^H (lower triangle) and the residual norm
+        const float rsq = rebuild_lower<NT, true>(U, ldu, lamp, d, n, GV, hs, phis, c1z, true);
+        float v[1] = {rsq};
+        block_sum<1>(v, red);
+        if (tid == 0) a.r_out[sig] = sqrtf(v[0]);
+    }
+}
+
 // =====================================================================================
 // k_mean: deterministic sum of r over the chunk (double), one CTA.
 //   out_sum[0] = sum, and if mean_out != null, mean_out[0] = float(sum / count_total).
