@@ -258,6 +258,11 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         const size_t sm = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (4 * ((d + 3) / 4)) * sizeof(float);
         CK(cudaFuncSetAttribute(k_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         prof::Scope pscope(prof::ROT, st);
+        static const bool fused = !(getenv("ADMMNET_ROTF") && atoi(getenv("ADMMNET_ROTF")) == 0);
+        if (fused) {      // same shared-memory size: ring of 4 x 256 entries instead of 2 x 512
+            CK(cudaFuncSetAttribute(k_rotf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_rotf<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
+        } else
         k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
         CK(cudaGetLastError());
     }

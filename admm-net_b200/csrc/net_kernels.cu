@@ -848,6 +848,158 @@ k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, in
     for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldr + (idx % d)];
 }
 
+// k_rotf: k_rot with PAIRS of consecutive sweeps fused.  k_rot is bound by shared-memory bandwidth (one 128-bit load
+// and one 128-bit store of a column of Z^T per rotation: 9 wavefronts of the 128 B/clk pipe, 4 signals per SM keep it
+// saturated).  Sweep B follows sweep A over (almost) the same columns, and rotation b_j only needs a_{j-1} to be
+// done, so B can trail A by one column with both carries in registers:
+//     step i:  load col i;  a_i on (col i, carryA = col i+1) -> outA = final col i+1 of A;
+//              b_{i+1} on (outA, carryB = col i+2) -> store col i+2;  carryB = new col i+1
+// i.e. one load and one store per TWO rotations.  Steps outside a sweep's own range are exact pass-throughs, so any
+// two ranges can be fused; pairs whose union is not shorter than 85 % of the two sweeps processed apart are not.
+// The stream is staged through a ring of four 256-entry buffers (two landed ahead of the read position, one in
+// flight), so both sweeps of a pair (<= 2(d+1) entries) are always resident.
+#define ROTF_STG 256
+__global__ void __launch_bounds__(ROT_THREADS)
+k_rotf(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zt,
+       const int* __restrict__ skip) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* ring = reinterpret_cast<float2*>(smem_raw);                   // [4][ROTF_STG]
+    float* z = reinterpret_cast<float*>(ring + 4 * ROTF_STG);             // [d][ldr]
+    const int ldr = 4 * ((d + 3) / 4);
+    const int lane = threadIdx.x;
+    const int sig = blockIdx.x;
+    if (skip && skip[sig]) return;
+    const float2* src = rot + (size_t)sig * rcap;
+    const int total = nrot[sig];
+    for (int idx = lane; idx < d * ldr; idx += 32) z[idx] = 0.f;
+    __syncwarp();
+    for (int r = lane; r < d; r += 32) z[r * ldr + r] = 1.f;
+    const int nstages = (total + ROTF_STG - 1) / ROTF_STG;
+    auto issue = [&](int k) {                                             // stage k -> ring slot k & 3 (one group)
+        if (k < nstages) {
+            const float2* g = src + (size_t)k * ROTF_STG;
+            float2* sdst = ring + (k & 3) * ROTF_STG;
+#pragma unroll
+            for (int q = lane; q < ROTF_STG / 2; q += 32) cp_async16(sdst + 2 * q, g + 2 * q);
+        }
+        cp_async_commit();
+    };
+    issue(0); issue(1); issue(2);
+    cp_async_wait<1>();                                                   // stages 0 and 1 have landed
+    __syncwarp();
+    int cur = 0;
+    const bool act = 4 * lane < ldr;
+    float4* zq = reinterpret_cast<float4*>(z) + (act ? lane : 0);        // column c at zq[c * lq]
+    const int lq = ldr / 4;
+#define RING(e) ring[(e) & (4 * ROTF_STG - 1)]
+    int q = 0;
+    while (q < total) {
+        while ((q / ROTF_STG) > cur) {                                    // entered a new stage: keep two landed ahead
+            ++cur;
+            __syncwarp();                                                 // every lane is done with stage cur-1
+            issue(cur + 2);
+            cp_async_wait<1>();
+            __syncwarp();
+        }
+        const float2 hA = RING(q);
+        const int mA = __float_as_int(hA.x);
+        if (mA < 0) break;
+        const int cntA = __float_as_int(hA.y);
+        const int qa = q + 1;
+        const int qB = qa + cntA;
+        bool pair = false;
+        int mB = 0, cntB = 0;
+        if (cntA > 0 && qB < total) {
+            const float2 hB = RING(qB);
+            mB = __float_as_int(hB.x);
+            cntB = __float_as_int(hB.y);
+            if (mB >= 0 && cntB > 0) {
+                const int top = max(mA, mB) - 1, end = min(mA - cntA, mB - cntB - 1);
+                pair = 20 * (top - end + 1) <= 17 * (cntA + cntB);
+            }
+        }
+        if (pair) {
+            const int qb = qB + 1;
+            const int lA = mA - cntA, lB = mB - cntB;
+            const int itop = max(mA, mB) - 1, iend = min(lA, lB - 1);
+            float4 cA = zq[(itop + 1) * lq], cB;
+            {   // first step: A only, its output is B's first carry
+                const float4 zi = zq[itop * lq];
+                if (itop <= mA - 1 && itop >= lA) {
+                    rot4(cB, cA, zi, RING(qa + mA - 1 - itop));
+                } else { cB = cA; cA = zi; }
+            }
+            int i = itop - 1;
+            // core: both sweeps active, two steps per trip, loads first
+            const int core_lo = max(lA, lB - 1);
+            const int core_hi = min(mA - 1, mB - 2);
+            // flagged steps above the core
+            for (; i >= iend && i > core_hi; --i) {
+                const float4 zi = i >= 0 ? zq[i * lq] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 oA, oB;
+                if (i <= mA - 1 && i >= lA) rot4(oA, cA, zi, RING(qa + mA - 1 - i)); else { oA = cA; cA = zi; }
+                if (i + 1 <= mB - 1 && i + 1 >= lB) rot4(oB, cB, oA, RING(qb + mB - 2 - i)); else { oB = cB; cB = oA; }
+                if (act) zq[(i + 2) * lq] = oB;
+            }
+            // (requesting the next trip's operands ahead of the FMA chain was measured slower: 376 -> 426 ms)
+            for (; i - 1 >= core_lo; i -= 2) {
+                const float2 ea0 = RING(qa + mA - 1 - i), ea1 = RING(qa + mA - i);
+                const float2 eb0 = RING(qb + mB - 2 - i), eb1 = RING(qb + mB - 1 - i);
+                const float4 z0 = zq[i * lq], z1 = zq[(i - 1) * lq];
+                float4 oA0, oB0, oA1, oB1;
+                rot4(oA0, cA, z0, ea0);
+                rot4(oB0, cB, oA0, eb0);
+                rot4(oA1, cA, z1, ea1);
+                rot4(oB1, cB, oA1, eb1);
+                if (act) { zq[(i + 2) * lq] = oB0; zq[(i + 1) * lq] = oB1; }
+            }
+            // flagged steps below (and the odd core step)
+            for (; i >= iend; --i) {
+                const float4 zi = i >= 0 ? zq[i * lq] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 oA, oB;
+                if (i <= mA - 1 && i >= lA) rot4(oA, cA, zi, RING(qa + mA - 1 - i)); else { oA = cA; cA = zi; }
+                if (i + 1 <= mB - 1 && i + 1 >= lB) rot4(oB, cB, oA, RING(qb + mB - 2 - i)); else { oB = cB; cB = oA; }
+                if (act) zq[(i + 2) * lq] = oB;
+            }
+            if (act) {
+                zq[(iend + 1) * lq] = cB;
+                if (iend >= 0) zq[iend * lq] = cA;
+            }
+            q = qb + cntB;
+        } else {
+            // single sweep (as k_rot): batches of 4 rotations, loads first
+            int col = mA;
+            float4 carry = zq[col * lq];
+            int t = 0;
+            for (; t + 4 <= cntA; t += 4) {
+                const float2 e0 = RING(qa + t), e1 = RING(qa + t + 1), e2 = RING(qa + t + 2), e3 = RING(qa + t + 3);
+                float4* zp = zq + (col - 1 - t) * lq;
+                const float4 z0 = zp[0], z1 = zp[-lq], z2 = zp[-2 * lq], z3 = zp[-3 * lq];
+                float4 o0, o1, o2, o3;
+                rot4(o0, carry, z0, e0);
+                rot4(o1, carry, z1, e1);
+                rot4(o2, carry, z2, e2);
+                rot4(o3, carry, z3, e3);
+                if (act) { zp[lq] = o0; zp[0] = o1; zp[-lq] = o2; zp[-2 * lq] = o3; }
+            }
+            for (; t < cntA; ++t) {
+                const float2 e = RING(qa + t);
+                float4* zp = zq + (col - 1 - t) * lq;
+                const float4 zi = zp[0];
+                float4 o;
+                rot4(o, carry, zi, e);
+                if (act) zp[lq] = o;
+            }
+            if (act) zq[(col - cntA) * lq] = carry;
+            q = qB;
+        }
+    }
+#undef RING
+    __syncwarp();
+    float* outz = Zt + (size_t)sig * d * d;
+    for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldr + (idx % d)];
+}
+
 // =====================================================================================
 // k_merge: one level of the divide & conquer merge tree.  Every range [a,b) of the level is the union of two
 // already-solved blocks torn at row p; eigenpairs of diag(D) + rho z z^T (z = Q^T v, poles D = block eigenvalues
