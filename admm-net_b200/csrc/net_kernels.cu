@@ -942,6 +942,30 @@ k_rotf(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, i
                 if (act) zq[(i + 2) * lq] = oB;
             }
             // (requesting the next trip's operands ahead of the FMA chain was measured slower: 376 -> 426 ms)
+            {
+                // fast form of the core loop: when neither sweep's parameters wrap around the ring inside this pair
+                // (4 pairs out of 5) plain pointers replace the masked index arithmetic (5 instead of 24 integer
+                // instructions per trip, and a lone warp pays two cycles for every instruction it issues)
+                const int ntr = i - 1 >= core_lo ? (i - core_lo + 1) / 2 : 0;
+                const int ia = (qa + mA - 1 - i) & (4 * ROTF_STG - 1), ib = (qb + mB - 2 - i) & (4 * ROTF_STG - 1);
+                if (ntr > 0 && ia + 2 * ntr <= 4 * ROTF_STG && ib + 2 * ntr <= 4 * ROTF_STG) {
+                    const float2* pa = ring + ia;
+                    const float2* pb = ring + ib;
+                    float4* zp = zq + i * lq;
+                    for (int tr = 0; tr < ntr; ++tr) {
+                        const float2 ea0 = pa[0], ea1 = pa[1], eb0 = pb[0], eb1 = pb[1];
+                        const float4 z0 = zp[0], z1 = zp[-lq];
+                        float4 oA0, oB0, oA1, oB1;
+                        rot4(oA0, cA, z0, ea0);
+                        rot4(oB0, cB, oA0, eb0);
+                        rot4(oA1, cA, z1, ea1);
+                        rot4(oB1, cB, oA1, eb1);
+                        if (act) { zp[2 * lq] = oB0; zp[lq] = oB1; }
+                        pa += 2; pb += 2; zp -= 2 * lq;
+                    }
+                    i -= 2 * ntr;
+                }
+            }
             for (; i - 1 >= core_lo; i -= 2) {
                 const float2 ea0 = RING(qa + mA - 1 - i), ea1 = RING(qa + mA - i);
                 const float2 eb0 = RING(qb + mB - 2 - i), eb1 = RING(qb + mB - 1 - i);
