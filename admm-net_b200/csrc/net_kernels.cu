@@ -952,17 +952,46 @@ k_rotf(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, i
                     const float2* pa = ring + ia;
                     const float2* pb = ring + ib;
                     float4* zp = zq + i * lq;
-                    for (int tr = 0; tr < ntr; ++tr) {
-                        const float2 ea0 = pa[0], ea1 = pa[1], eb0 = pb[0], eb1 = pb[1];
-                        const float4 z0 = zp[0], z1 = zp[-lq];
-                        float4 oA0, oB0, oA1, oB1;
-                        rot4(oA0, cA, z0, ea0);
-                        rot4(oB0, cB, oA0, eb0);
-                        rot4(oA1, cA, z1, ea1);
-                        rot4(oB1, cB, oA1, eb1);
-                        if (act) { zp[2 * lq] = oB0; zp[lq] = oB1; }
-                        pa += 2; pb += 2; zp -= 2 * lq;
+                    // two register sets: the loads of trip t+1 are issued before the FMA chain of trip t (pure
+                    // reordering, no extra instructions; a load past the last trip reads valid, unused shared memory)
+#define ROTF_LD(S, K)                                                                          \
+    const float2 ea0##S = pa[2 * (K)], ea1##S = pa[2 * (K) + 1], eb0##S = pb[2 * (K)], eb1##S = pb[2 * (K) + 1]; \
+    const float4 z0##S = zp[-2 * (K) * lq], z1##S = zp[-(2 * (K) + 1) * lq];
+#define ROTF_DO(S, K)                                                                          \
+    {                                                                                          \
+        float4 oA0, oB0, oA1, oB1;                                                             \
+        rot4(oA0, cA, z0##S, ea0##S);                                                          \
+        rot4(oB0, cB, oA0, eb0##S);                                                            \
+        rot4(oA1, cA, z1##S, ea1##S);                                                          \
+        rot4(oB1, cB, oA1, eb1##S);                                                            \
+        if (act) { zp[(2 - 2 * (K)) * lq] = oB0; zp[(1 - 2 * (K)) * lq] = oB1; }               \
+    }
+                    int tr = 0;
+                    for (; tr + 4 <= ntr; tr += 4) {
+                        ROTF_LD(X, 0)
+                        ROTF_LD(Y, 1)
+                        ROTF_LD(V, 2)
+                        ROTF_LD(W, 3)
+                        ROTF_DO(X, 0)
+                        ROTF_DO(Y, 1)
+                        ROTF_DO(V, 2)
+                        ROTF_DO(W, 3)
+                        pa += 8; pb += 8; zp -= 8 * lq;
                     }
+                    if (tr + 2 <= ntr) {
+                        ROTF_LD(X, 0)
+                        ROTF_LD(Y, 1)
+                        ROTF_DO(X, 0)
+                        ROTF_DO(Y, 1)
+                        pa += 4; pb += 4; zp -= 4 * lq;
+                        tr += 2;
+                    }
+                    if (tr < ntr) {
+                        ROTF_LD(X, 0)
+                        ROTF_DO(X, 0)
+                    }
+#undef ROTF_LD
+#undef ROTF_DO
                     i -= 2 * ntr;
                 }
             }
