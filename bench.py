@@ -37,7 +37,8 @@ BYTES_PER_SIGNAL = 2404          # y 800 + b 800 + sigma 4 in, phi 800 out
 # implementation DRAM traffic of the layer kernels per signal-layer, from the ncu --set full capture in
 # profiles/r01_ncu_summary.md (dram__bytes_read+write over 4096 signals): k_head 180 + k_head2 (4 stages) 174 +
 # k_ql 56 + k_rot 102 + k_tail 114 KB
-TRAFFIC_PER_SIGNAL_LAYER = 626e3
+TRAFFIC_PER_SIGNAL_LAYER = 626e3      # general layer (k_head .. k_tail_p), ncu dram read+write per signal
+TRAFFIC_ARROW_LAYER = 71e3            # layer 0 through k_arrow
 
 
 def tile_signals(B, seed):
@@ -363,8 +364,8 @@ def main():
             "bound": "fp32", "kernel": "layer pipeline k_head+k_head2+k_ql+k_rot+k_tail (dominant: %s)" % dom,
             "forward_ms_per_step": fwd_ms,
             "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
-            "traffic": TRAFFIC_PER_SIGNAL_LAYER * (K_LAYERS - 1) * B,
-            "traffic_note": "bytes per step of the four layer kernels (profiles/r01_ncu_summary.md); algorithmic "
+            "traffic": (TRAFFIC_PER_SIGNAL_LAYER * (K_LAYERS - 2) + TRAFFIC_ARROW_LAYER) * B,
+            "traffic_note": "bytes per step of the layer kernels (ncu dram read+write, profiles/r01_ncu_summary.md: layer 0 through k_arrow, 8 general layers); algorithmic "
                             "bytes per step are 2404 B x signals: the path is compute bound, the extra traffic is "
                             "per-layer state (packed Z, G, reflectors, rotation stream) at <5 % of HBM bandwidth",
             "note": "FP32-FMA/shared-memory bound eigen-solver (SURVEY.md §8d): algorithmic 33.1 MFLOP per signal-layer x "
