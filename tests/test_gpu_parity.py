@@ -447,18 +447,22 @@ def test_admmnet_full_module_matches_reference_golden(pkg):
     np.testing.assert_allclose(t3.cpu().numpy(), z["tau"][:5], atol=2e-6, rtol=1e-5)
 
 
-def test_layer0_shortcut_and_general_path_agree(pkg, tmp_path):
-    """The same forward with the arrowhead shortcut (default) and with ADMMNET_ARROW=0 (dense eigen-solver at layer 0
-    too; the switch is read once per process, hence the subprocess)."""
+@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILP", "ADMMNET_LANES"])
+def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
+    """Every fast path has a plain sibling behind an environment switch (read once per process, hence the
+    subprocess): ADMMNET_ARROW=0 dense eigen-solver at layer 0 instead of the arrowhead shortcut, ADMMNET_ROTF=0
+    one sweep at a time in the rotation kernel, ADMMNET_TAILP=0 non-persistent back-transformation,
+    ADMMNET_LANES=0 single stream.  Same inputs, same answer."""
     import subprocess
     import sys
     z, sd = load_net_case("pert_k10")
     net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
     net.load_state_dict(sd)
     y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
+    yy, bb, ss = y.repeat(300, 1), b.repeat(300, 1), s.repeat(300)        # 2100 signals: the large-batch (QL) path
     with torch.no_grad():
-        phi = net(y, b, s).numpy()
-    out = str(tmp_path / "phi_general.npy")
+        phi = net(yy, bb, ss).numpy()
+    out = str(tmp_path / "phi_alt.npy")
     code = (
         "import sys, numpy as np, torch\n"
         f"sys.path.insert(0, {ROOT!r})\n"
@@ -468,9 +472,12 @@ def test_layer0_shortcut_and_general_path_agree(pkg, tmp_path):
         "net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval(); net.load_state_dict(sd)\n"
         "y, b, s = (torch.from_numpy(z[k]) for k in ('y', 'b', 'sigma'))\n"
         "with torch.no_grad():\n"
-        f"    np.save({out!r}, net(y, b, s).numpy())\n")
-    env = dict(os.environ, ADMMNET_ARROW="0")
+        f"    np.save({out!r}, net(y.repeat(300, 1), b.repeat(300, 1), s.repeat(300)).numpy())\n")
+    env = dict(os.environ)
+    env[switch] = "0"
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
-    phi_general = np.load(out)
-    assert rel_err(phi, phi_general).max() < 3e-5
-    assert rel_err(phi_general, z["phi_batch"]).max() < PHI_TOL
+    phi_alt = np.load(out)
+    assert rel_err(phi, phi_alt).max() < 3e-5
+    # a batch of 300 copies of the 7 golden signals has the same batch mean as the 7 signals themselves
+    assert rel_err(phi_alt[:7], z["phi_batch"]).max() < PHI_TOL
+    assert rel_err(phi[:7], z["phi_batch"]).max() < PHI_TOL
