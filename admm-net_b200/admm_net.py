@@ -233,11 +233,27 @@ class PeakSearchLayer(nn.Module):
                                                         nn.Tanh()) for _ in range(L)])
         self.confidence_net = nn.Sequential(nn.Linear(hidden_dim // 8, 16), nn.ReLU(), nn.Linear(16, 1), nn.Sigmoid())
 
+    def forward(self, phi, b=None):
+        """admm_net.py:570-630 as a differentiable torch graph (the TRAINING path of the head, attention dropout
+        included in train mode); inference goes through the fused kernel, ADMMNet.head_device."""
+        B = phi.shape[0]
+        x = self.feature_extractor(torch.cat([phi.real, phi.imag], dim=1))
+        pos = self.position_projection(self.position_encoder.unsqueeze(0).repeat(B, 1, 1))
+        attended, _ = self.attention(query=x.unsqueeze(1), key=pos, value=pos)
+        x_peak = self.peak_extractor(x + attended.squeeze(1))
+        taus, fs, confs = [], [], []
+        for t in range(self.L_max):
+            feat = x_peak + torch.tensor(t / self.L_max, device=phi.device)
+            taus.append(self.tau_regressor[t](feat))
+            fs.append(self.f_regressor[t](feat))
+            confs.append(self.confidence_net(feat))
+        return torch.cat(taus, dim=1), torch.cat(fs, dim=1), torch.cat(confs, dim=1)
+
 
 class ADMMNet(PhiEstADMMNet):
     """admm_net.py:767-816.  forward(y, b, sigma) -> (tau_est, f_est, confidences, phi): the unrolled loop is shared
-    with PhiEstADMMNet; the PeakSearchLayer head (admm_net.py:570-630) runs in csrc/head_kernels.cu with eval-mode
-    semantics (no attention dropout)."""
+    with PhiEstADMMNet; in eval mode the PeakSearchLayer head (admm_net.py:570-630) runs in csrc/head_kernels.cu (no
+    attention dropout), in train() mode with grad enabled the whole forward is differentiable (forward_differentiable)."""
 
     def __init__(self, M, N, L=3, num_layers=10):
         super().__init__(M, N, L, num_layers)
@@ -265,13 +281,24 @@ class ADMMNet(PhiEstADMMNet):
                                                   f.data_ptr(), conf.data_ptr(), stream))
         return tau, f, conf
 
+    def forward_differentiable(self, y, b, sigma, _eigh=None):
+        """train.py:177-201: the unrolled layers as the autograd graph around the CUDA eigen-solver (autograd.py) and
+        the head as torch modules.  `_eigh` is the CPU test hook of forward_train."""
+        from .autograd import forward_train
+        phi = forward_train(self, y, b, sigma, _eigh)
+        tau, f, conf = self.peakSearchLayer(phi, b)
+        return tau, f, conf, phi
+
     def forward(self, y, b, sigma):
-        if self.training and not self._warned:
-            warnings.warn("admmnet_b200: ADMMNet runs its head with eval-mode semantics (no attention dropout)")
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         src_dev = y.device
         yd, bd, sd, _ = self._prep(y, b, sigma)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and not self._warned:
-            warnings.warn("admmnet_b200: forward is an inference fast path; the result is detached from autograd")
+        if needs_grad and self.training:
+            outs = self.forward_differentiable(yd, bd, sd)
+            return outs if src_dev.type == "cuda" else tuple(t.to(src_dev) for t in outs)
+        if needs_grad and not self._warned:
+            warnings.warn("admmnet_b200: eval-mode forward is the inference fast path; the result is detached from "
+                          "autograd (call model.train() for the differentiable path)")
             self._warned = True
         phi = self.forward_device(yd, bd, sd)
         tau, f, conf = self.head_device(phi)

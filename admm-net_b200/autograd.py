@@ -127,3 +127,33 @@ class PhiAlignmentLoss(torch.nn.Module):
         phase_loss = F.mse_loss(diff, torch.zeros_like(diff))
         total = self.amplitude_weight * amplitude_loss + self.phase_weight * phase_loss
         return total, {"total_loss": total, "amplitude_loss": amplitude_loss, "phase_loss": phase_loss}
+
+
+def basic_parameter_loss(tau_pred, f_pred, tau_true, f_true, confidences, L_true):
+    """loss.py:6-30 without the per-sample Python loop: for a sample with L true targets the MSE of the first L
+    (tau, f) pairs plus 0.1 * MSE(confidence[:L], 1); with L = 0 the sum of squared confidences; batch mean."""
+    B, Lmax = tau_pred.shape
+    L = L_true.to(tau_pred.device).reshape(B, 1)
+    mask = (torch.arange(Lmax, device=tau_pred.device).unsqueeze(0) < L).to(tau_pred.dtype)
+    cnt = L.clamp(min=1).to(tau_pred.dtype)
+    tau_loss = (mask * (tau_pred - tau_true) ** 2).sum(1, keepdim=True) / cnt
+    f_loss = (mask * (f_pred - f_true) ** 2).sum(1, keepdim=True) / cnt
+    conf_loss = (mask * (confidences - 1.0) ** 2).sum(1, keepdim=True) / cnt
+    with_targets = tau_loss + f_loss + 0.1 * conf_loss
+    without = (confidences ** 2).sum(1, keepdim=True)
+    return torch.where(L > 0, with_targets, without).sum() / B
+
+
+class BasicANMLoss(torch.nn.Module):
+    """loss.py:33-59 (train.py's criterion): parameter loss + lambda_reg * mean ||phi||."""
+
+    def __init__(self, lambda_reg=1e-4):
+        super().__init__()
+        self.lambda_reg = lambda_reg
+
+    def forward(self, model_outputs, ground_truth):
+        param_loss = basic_parameter_loss(model_outputs["tau_est"], model_outputs["f_est"], ground_truth["tau_true"],
+                                          ground_truth["f_true"], model_outputs["confidences"], ground_truth["L_true"])
+        reg_loss = self.lambda_reg * torch.mean(torch.norm(model_outputs["phi_final"], dim=1))
+        total = param_loss + reg_loss
+        return total, {"total_loss": total, "param_loss": param_loss, "reg_loss": reg_loss}

@@ -171,6 +171,28 @@ def main():
              **{"sd__" + k_: v_ for k_, v_ in sd_to_npz(tm.state_dict()).items()})
     print("train loss", float(total), "params with grad", sum(v_.size > 0 for v_ in grads.values()), "of", len(grads))
 
+    # ------------------------------------------------------------------ train.py: ADMMNet + BasicANMLoss gradients
+    # (eval mode = attention dropout off, so the numbers are reproducible; grad enabled)
+    torch.manual_seed(6)
+    fm = admm_net.ADMMNet(10, 10, 3, 3).eval()
+    perturb_(fm, 11)
+    torch.manual_seed(7)
+    tau_t, f_t = torch.rand(7, 3) * 0.8 + 0.1, torch.rand(7, 3) * 0.8 - 0.4
+    L_t = torch.tensor([3, 2, 0, 1, 3, 3, 2])
+    tau_e, f_e, conf_e, phi_e = fm(ty, tb, ts)
+    crit2 = ref_loss.BasicANMLoss()
+    tot2, parts2 = crit2({"tau_est": tau_e, "f_est": f_e, "confidences": conf_e, "phi_final": phi_e},
+                         {"tau_true": tau_t, "f_true": f_t, "L_true": L_t, "y": ty, "b": tb})
+    tot2.backward()
+    grads2 = {n_.replace(".", "__"): (p_.grad.numpy() if p_.grad is not None else np.zeros(0, np.float32))
+              for n_, p_ in fm.named_parameters()}
+    np.savez(os.path.join(HERE, "train_full_grads_k3.npz"), y=y_all, b=b_all, sigma=s_all, K=3, tau_true=tau_t.numpy(),
+             f_true=f_t.numpy(), L_true=L_t.numpy(), loss=float(tot2), param_loss=float(parts2["param_loss"]),
+             reg_loss=float(parts2["reg_loss"]), tau=tau_e.detach().numpy(), f=f_e.detach().numpy(),
+             conf=conf_e.detach().numpy(), **{"grad__" + k_: v_ for k_, v_ in grads2.items()},
+             **{"sd__" + k_: v_ for k_, v_ in sd_to_npz(fm.state_dict()).items()})
+    print("ADMMNet train loss", float(tot2), "params with grad", sum(v_.size > 0 for v_ in grads2.values()), "of", len(grads2))
+
     # ------------------------------------------------------------------ full ADMMNet (unrolled loop + PeakSearchLayer head)
     torch.manual_seed(3)
     full = admm_net.ADMMNet(10, 10, 3, 3).eval()
