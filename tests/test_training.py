@@ -337,3 +337,24 @@ def test_admmnet_training_gradients_match_reference_gpu():
     y, b, s = (torch.from_numpy(z[k]).cuda() for k in ("y", "b", "sigma"))
     tau, f, conf, phi = model(y, b, s)
     assert tau.requires_grad and phi.requires_grad and tau.shape == (7, 3)
+
+
+def test_save_dataset_round_trip_and_no_cpu_generation(tmp_path):
+    from admmnet_b200 import _capi
+    from admmnet_b200.dataset import FIELDS, generate_dataset, load_split, save_dataset, split_sizes
+    assert split_sizes(10000) == (7000, 1500, 1500) and split_sizes(7, 0.7, 0.15) == (4, 1, 2)   # generate_data.py:54-57
+    raw = {}
+    rng = np.random.default_rng(1)
+    for name, n in (("train", 5), ("val", 2), ("test", 1)):
+        raw[name] = {k: (np.full((n,), 3, np.int32) if k == "L_true" else
+                         rng.standard_normal((n,) if k in ("sigma", "ser") else (n, 3) if k in ("tau", "f", "C_real", "C_imag")
+                                             else (n, 100)).astype(np.float32)) for k in FIELDS}
+    save_dataset(str(tmp_path), raw, {"Nb": 10, "Nd": 10, "L_max": 3, "snr_range": [5, 25], "total_samples": 8})
+    assert json.load(open(tmp_path / "dataset_config.json"))["total_samples"] == 8
+    assert (tmp_path / "dataset_info.npz").exists()
+    y, b, tau, f, C, L_true, sigma, phi = load_split(str(tmp_path), "val")
+    assert np.array_equal(phi.numpy(), raw["val"]["phi_real"] + 1j * raw["val"]["phi_imag"])
+    assert np.array_equal(tau.numpy(), raw["val"]["tau"]) and L_true.tolist() == [3, 3]
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.AdmmnetError):                 # the writer is a device path: no CPU fallback
+            generate_dataset(str(tmp_path / "x"), total_samples=10)
