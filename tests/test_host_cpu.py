@@ -248,3 +248,47 @@ def test_global_norm_scope_two_ranks_gloo():
         ref = net_oracle.forward(sd, y[lo:hi], b[lo:hi], s[lo:hi], 10, 10, int(z["K"])).numpy()
         assert rel_err(out["shard"], ref).max() < 5e-5
     assert rel_err(np.concatenate([r[3]["shard"] for r in res]), z["phi_batch"]).max() > 1e-4
+
+
+def test_arrowhead_algorithm_emulation_is_backward_stable():
+    """The layer-0 shortcut's algorithm (fp32 emulation of csrc/arrow_kernels.cu, tests/arrow_emulation.py) on
+    adversarial arrowheads: clustered and nearly repeated poles, weak and mixed couplings, a corner element below
+    every pole, large pole scale.  Residual and orthogonality stay at fp32 rounding in every case."""
+    from tests.arrow_emulation import arrow_eigh
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    done = 0
+    for trial in range(32):
+        n = int(rng.choice([3, 7, 20, 40]))
+        kind = trial % 8
+        h = (rng.standard_normal(n) * 0.1).astype(f32)
+        phi = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        c0 = f32(1.8)
+        if kind == 1:
+            h = (np.sort(rng.random(n)) * 1e-3).astype(f32)
+        elif kind == 2:
+            h, phi = (h * f32(0.01)).astype(f32), (phi * 3).astype(np.complex64)
+        elif kind == 3:
+            phi = (phi * f32(1e-3)).astype(np.complex64)
+        elif kind == 4:
+            phi[::2] *= f32(1e-4)
+        elif kind == 5:
+            c0 = f32(rng.standard_normal() * 5)
+        elif kind == 6:
+            h = (h * f32(100)).astype(f32)
+        elif kind == 7:
+            h = (np.round(h * 1e3) / 1e3 + np.arange(n) * 1e-7).astype(f32)       # nearly repeated poles
+        if len(np.unique(h)) < n:
+            continue
+        res = arrow_eigh(h, phi, c0)
+        assert res is not None, (trial, kind, n)
+        lam, U = res
+        A = np.zeros((n + 1, n + 1), np.complex128)
+        A[:n, :n] = np.diag(h.astype(float))
+        A[:n, n], A[n, :n], A[n, n] = phi, np.conj(phi), c0
+        sc = np.linalg.norm(A, 2)
+        assert np.abs(A @ U - U * lam[None, :]).max() / sc < 2e-6, (trial, kind, n)
+        assert np.abs(U.conj().T @ U - np.eye(n + 1)).max() < 3e-6, (trial, kind, n)
+        assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() / sc < 1e-6, (trial, kind, n)
+        done += 1
+    assert done >= 28
