@@ -292,3 +292,31 @@ def test_arrowhead_algorithm_emulation_is_backward_stable():
         assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() / sc < 1e-6, (trial, kind, n)
         done += 1
     assert done >= 28
+
+
+def test_fused_sweep_schedule_equals_sequential_sweeps_for_every_range_pair():
+    """k_rotf applies two consecutive QL sweeps in one pass (sweep B one column behind sweep A, out-of-range steps as
+    pass-throughs).  Emulation of that schedule (tests/rotf_emulation.py) against the two sweeps applied one after
+    the other, for EVERY pair of column ranges of a 9x9 problem — nested, overlapping, disjoint, B above A, B reaching
+    column 0 — whether or not the kernel's 85 % rule would pair them."""
+    from tests.rotf_emulation import apply_pair, apply_single, would_pair
+    d = 9
+    rng = np.random.default_rng(0)
+    Z0 = rng.standard_normal((5, d))
+    n_pairs = n_rule = 0
+    for mA in range(1, d):
+        for cntA in range(1, mA + 1):
+            for mB in range(1, d):
+                for cntB in range(1, mB + 1):
+                    ang = rng.uniform(-np.pi, np.pi, cntA + cntB)
+                    pa = [(np.cos(a), np.sin(a)) for a in ang[:cntA]]
+                    pb = [(np.cos(a), np.sin(a)) for a in ang[cntA:]]
+                    ref = Z0.copy()
+                    apply_single(ref, mA, pa)
+                    apply_single(ref, mB, pb)
+                    got = Z0.copy()
+                    apply_pair(got, mA, pa, mB, pb)
+                    assert np.abs(got - ref).max() < 1e-12, (mA, cntA, mB, cntB)
+                    n_pairs += 1
+                    n_rule += would_pair(mA, cntA, mB, cntB)
+    assert n_pairs == 1296 and 0 < n_rule < n_pairs
