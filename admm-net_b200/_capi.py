@@ -14,6 +14,7 @@ _PROTOS = {
     "admmnet_forward_workspace_bytes": (_i, [_i, _i, _i, _i, _i, C.POINTER(_sz)]),
     "admmnet_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "admmnet_layer_chunk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "admmnet_layer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "admmnet_layer_rsum": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "admmnet_ws_scalars": (_i, [_vp, _sz, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "admmnet_set_mean": (_i, [_vp, _sz, _i, _i, _i, _i, _i, _i, _d, _vp]),
@@ -35,6 +36,7 @@ _PROTOS = {
     "admmnet_profile_kinds": (_i, []),
     "admmnet_profile_kind_name": (C.c_char_p, [_i]),
     "admmnet_profile_end": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
+    "admmnet_tc_gemm_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "admmnet_fp32_peak_launch": (_i, [_vp, _i, _i, C.POINTER(_d), _vp]),
 }
 EXPORTS = tuple(_PROTOS)

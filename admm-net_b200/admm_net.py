@@ -160,33 +160,42 @@ class PhiEstADMMNet(nn.Module):
         P = self.packed_params(dev)
         if out is None:
             out = torch.empty(B, n, dtype=torch.complex64, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
         chunk = min(self.chunk, B)
-        if self.norm_scope == "batch":
-            ws = self.workspace(B, chunk, dev)
-            _capi.check(L.admmnet_forward(y.data_ptr(), b.data_ptr(), sigma.data_ptr(), B, chunk, self.M, self.N, K,
-                                          P.data_ptr(), out.data_ptr(), ws.ptr, ws.nbytes, self.rcap, stream))
-            self._status(ws, stream)
-        elif self.norm_scope == "chunk":
-            for off in range(0, B, chunk):
-                Bc = min(chunk, B - off)
-                ws = self.workspace(Bc, Bc, dev)
-                _capi.check(L.admmnet_forward(y[off:].data_ptr(), b[off:].data_ptr(), sigma[off:].data_ptr(), Bc, Bc,
-                                              self.M, self.N, K, P.data_ptr(), out[off:].data_ptr(), ws.ptr, ws.nbytes,
-                                              self.rcap, stream))
-                self._status(ws, stream)
-        else:
-            raise ValueError("norm_scope must be 'batch' or 'chunk' (use sharding.sharded_forward for 'global')")
+        # the library keys its lane streams by cudaGetDevice(): make the tensors' device current for the calls
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if self.norm_scope == "batch":
+                ws = self.workspace(B, chunk, dev)
+                _capi.check(L.admmnet_forward(y.data_ptr(), b.data_ptr(), sigma.data_ptr(), B, chunk, self.M, self.N,
+                                              K, P.data_ptr(), out.data_ptr(), ws.ptr, ws.nbytes, self.rcap, stream))
+                self._status(ws, stream, B, chunk)
+            elif self.norm_scope == "chunk":
+                # one workspace sized for a full chunk serves the ragged tail too (the C ABI only needs
+                # ws_bytes >= what (Bc, Bc) asks for)
+                ws = self.workspace(chunk, chunk, dev)
+                bad = 0
+                for off in range(0, B, chunk):
+                    Bc = min(chunk, B - off)
+                    _capi.check(L.admmnet_forward(y[off:].data_ptr(), b[off:].data_ptr(), sigma[off:].data_ptr(), Bc,
+                                                  Bc, self.M, self.N, K, P.data_ptr(), out[off:].data_ptr(), ws.ptr,
+                                                  ws.nbytes, self.rcap, stream))
+                    bad |= self._status(ws, stream, Bc, Bc, raise_=False)   # every forward resets the status word
+                if bad:
+                    raise _capi.AdmmnetError(f"eigen-solver reported status {bad} (QL non-convergence / stream overflow)")
+            else:
+                raise ValueError("norm_scope must be 'batch' or 'chunk' (use sharding.sharded_forward for 'global')")
         return out
 
-    def _status(self, ws, stream):
+    def _status(self, ws, stream, B=None, chunk=None, raise_=True):
         if not self.check_status:
-            return
+            return 0
         st = C.c_int(0)
-        _capi.check(_capi.lib().admmnet_status(ws.ptr, ws.nbytes, ws.B, ws.chunk, ws.n, ws.K, ws.rcap, stream,
+        _capi.check(_capi.lib().admmnet_status(ws.ptr, ws.nbytes, ws.B if B is None else B,
+                                               ws.chunk if chunk is None else chunk, ws.n, ws.K, ws.rcap, stream,
                                                C.byref(st)))
-        if st.value:
+        if st.value and raise_:
             raise _capi.AdmmnetError(f"eigen-solver reported status {st.value} (QL non-convergence / stream overflow)")
+        return st.value
 
     def forward(self, y, b, sigma):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
@@ -276,9 +285,10 @@ class ADMMNet(PhiEstADMMNet):
         dev = phi.device
         H = self.packed_head(dev)
         tau, f, conf = (torch.empty(B, L, dtype=torch.float32, device=dev) for _ in range(3))
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _capi.check(_capi.lib().admmnet_peak_head(phi.contiguous().data_ptr(), B, n, L, H.data_ptr(), tau.data_ptr(),
-                                                  f.data_ptr(), conf.data_ptr(), stream))
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib().admmnet_peak_head(phi.contiguous().data_ptr(), B, n, L, H.data_ptr(),
+                                                      tau.data_ptr(), f.data_ptr(), conf.data_ptr(), stream))
         return tau, f, conf
 
     def forward_differentiable(self, y, b, sigma, _eigh=None):

@@ -2,7 +2,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/admmnet_b200.h"
@@ -12,6 +15,7 @@
 #include "peak_kernels.cu"
 #include "gen_kernels.cu"
 #include "head_kernels.cu"
+#include "tc_probe.cu"
 
 using namespace admmnet;
 
@@ -29,12 +33,13 @@ static int fail(int code, const std::string& msg) {
 
 // ------------------------------------------------------------------------------------ profiling hooks
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
-// Process-global, not thread safe; off by default (then the only cost is one branch per launch).
+// Process-global (guarded by a mutex); off by default (then the only cost is one branch per launch).
 namespace prof {
 enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, ARROW, NKINDS };
 static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge", "k_arrow"};
 struct Rec { int kind; cudaEvent_t a, b; };
 static bool on = false;
+static std::mutex mu;               // launches may come from several host threads while profiling is on
 static std::vector<Rec> recs;
 static std::vector<cudaEvent_t> pool;
 static size_t pool_used = 0;
@@ -49,15 +54,18 @@ static cudaEvent_t get_event() {
 struct Scope {
     cudaStream_t st;
     bool active;
+    cudaEvent_t eb = nullptr;
     Scope(int kind, cudaStream_t s) : st(s), active(on) {
         if (active) {
+            std::lock_guard<std::mutex> lock(mu);
             Rec r{kind, get_event(), get_event()};
+            eb = r.b;
             cudaEventRecord(r.a, st);
             recs.push_back(r);
         }
     }
     ~Scope() {
-        if (active) cudaEventRecord(recs.back().b, st);
+        if (active) cudaEventRecord(eb, st);
     }
 };
 }  // namespace prof
@@ -118,23 +126,28 @@ static int nslot_value() {
 #define NSLOT (nslot_value())
 constexpr int TR_MAX = 88;   // largest trailing block handed to a later tridiagonalisation stage
 // orders at which the trailing block is compacted and handed to the next (smaller, higher-occupancy) stage
-inline int next_stage_order(int d) {
-    static int marks[8] = {80, 64, 48, 32, 0, 0, 0, 0};
-    static bool init = false;
-    if (!init) {                                   // ADMMNET_STAGES="88,72,56,40" overrides the plan (tuning)
-        init = true;
-        if (const char* e = getenv("ADMMNET_STAGES")) {
+struct StagePlan { int marks[8]; };
+inline const StagePlan& stage_plan() {
+    // parsed once; C++11 guarantees the initialisation of a function-local static is thread safe
+    static const StagePlan plan = [] {
+        StagePlan p = {{80, 64, 48, 32, 0, 0, 0, 0}};
+        if (const char* e = getenv("ADMMNET_STAGES")) {   // ADMMNET_STAGES="88,72,56,40" overrides the plan (tuning)
             int n = 0;
-            for (const char* p = e; *p && n < 7;) {
-                marks[n++] = atoi(p);
-                while (*p && *p != ',') ++p;
-                if (*p == ',') ++p;
+            for (const char* q = e; *q && n < 7;) {
+                p.marks[n++] = atoi(q);
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
             }
-            for (; n < 8; ++n) marks[n] = 0;
+            for (; n < 8; ++n) p.marks[n] = 0;
         }
-    }
-    for (int i = 0; i < 8 && marks[i] > 0; ++i)
-        if (marks[i] <= TR_MAX && d > marks[i] + 8) return marks[i];
+        return p;
+    }();
+    return plan;
+}
+inline int next_stage_order(int d) {
+    const StagePlan& p = stage_plan();
+    for (int i = 0; i < 8 && p.marks[i] > 0; ++i)
+        if (p.marks[i] <= TR_MAX && d > p.marks[i] + 8) return p.marks[i];
     return 0;     // finish in this stage
 }
 inline int stage1_steps(int d) { const int nx = next_stage_order(d); return nx ? d - nx : d - 1; }
@@ -372,36 +385,40 @@ extern "C" int admmnet_ws_scalars(void* ws, size_t ws_bytes, int B, int chunk, i
     return 0;
 }
 
-// Internal streams for admmnet_forward: two chunk lanes (consecutive chunks of a layer overlap) and one
-// high-priority side stream per lane for the latency-bound k_ql.  Created lazily, one set per device.
+// Internal streams for admmnet_forward: chunk lanes (consecutive chunks of a layer overlap) and one
+// high-priority side stream per lane for the latency-bound k_ql.  One set per (device, caller stream), created
+// lazily under a mutex: calls from different host threads on different streams (with their own workspaces) never
+// share a stream or an event, so admmnet_forward is re-entrant across streams as the header states.  Two threads
+// enqueueing on the SAME stream would interleave their launches and is not supported (as for any CUDA library).
 namespace {
 struct Lanes {
-    bool init = false;
     cudaStream_t L[NSLOT_MAX], Q[NSLOT_MAX];
     cudaEvent_t evH[NSLOT_MAX], evQ[NSLOT_MAX], evDone[NSLOT_MAX], evStart, evMean, evEnd;
 };
-Lanes g_lanes[16];
-int get_lanes(Lanes** out) {
+std::mutex g_lanes_mu;
+std::map<std::pair<int, cudaStream_t>, Lanes*> g_lanes;
+int get_lanes(cudaStream_t caller, Lanes** out) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return fail(ADMMNET_ERR_ARG, "device ordinal out of range");
-    Lanes& l = g_lanes[dev];
-    if (!l.init) {
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        for (int i = 0; i < NSLOT; ++i) {
-            CK(cudaStreamCreateWithPriority(&l.L[i], cudaStreamNonBlocking, lo));
-            CK(cudaStreamCreateWithPriority(&l.Q[i], cudaStreamNonBlocking, hi));
-            CK(cudaEventCreateWithFlags(&l.evH[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&l.evQ[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&l.evDone[i], cudaEventDisableTiming));
-        }
-        CK(cudaEventCreateWithFlags(&l.evStart, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&l.evMean, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&l.evEnd, cudaEventDisableTiming));
-        l.init = true;
+    std::lock_guard<std::mutex> lock(g_lanes_mu);
+    auto key = std::make_pair(dev, caller);
+    auto it = g_lanes.find(key);
+    if (it != g_lanes.end()) { *out = it->second; return 0; }
+    Lanes* l = new Lanes();
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < NSLOT; ++i) {
+        CK(cudaStreamCreateWithPriority(&l->L[i], cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&l->Q[i], cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&l->evH[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l->evQ[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l->evDone[i], cudaEventDisableTiming));
     }
-    *out = &l;
+    CK(cudaEventCreateWithFlags(&l->evStart, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l->evMean, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l->evEnd, cudaEventDisableTiming));
+    g_lanes[key] = l;
+    *out = l;
     return 0;
 }
 }  // namespace
@@ -519,6 +536,55 @@ extern "C" int admmnet_final_phi(const void* y, const void* b, int B, int chunk,
     return 0;
 }
 
+// all chunks of layer k over the lanes (which must already be ordered after the producer of the layer's inputs),
+// joined on lane 0 where the residual norms are summed
+static int layer_over_lanes(Lanes* ln, const void* y, const void* b, const float* sigma, int B, int chunk, int Mdim,
+                            int Ndim, int K, int k, const float* params, void* ws, size_t ws_bytes, int rcap) {
+    const int n = Mdim * Ndim;
+    int c = 0;
+    for (int off = 0; off < B; off += chunk, ++c) {
+        const int Bc = B - off < chunk ? B - off : chunk;
+        const int s = c % NSLOT;
+        if (int e = layer_chunk_impl(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
+                                     ln->L[s], s, ln->Q[s], ln->evH[s], ln->evQ[s]))
+            return e;
+    }
+    for (int i = 1; i < NSLOT; ++i) {
+        CK(cudaEventRecord(ln->evDone[i], ln->L[i]));
+        CK(cudaStreamWaitEvent(ln->L[0], ln->evDone[i], 0));
+    }
+    return admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, ln->L[0]);
+}
+
+static bool lanes_enabled() {
+    static const bool use_lanes = !(getenv("ADMMNET_LANES") && atoi(getenv("ADMMNET_LANES")) == 0);
+    return use_lanes;
+}
+
+extern "C" int admmnet_layer(const void* y, const void* b, const float* sigma, int B, int chunk, int Mdim, int Ndim,
+                             int K, int k, const float* params, void* ws, size_t ws_bytes, int rcap, void* stream) {
+    const int n = Mdim * Ndim;
+    if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (!lanes_enabled()) {
+        for (int off = 0; off < B; off += chunk) {
+            const int Bc = B - off < chunk ? B - off : chunk;
+            if (int e = admmnet_layer_chunk(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
+                                            stream))
+                return e;
+        }
+        return admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, stream);
+    }
+    Lanes* ln = nullptr;
+    if (int e = get_lanes(cs, &ln)) return e;
+    CK(cudaEventRecord(ln->evStart, cs));
+    for (int i = 0; i < NSLOT; ++i) CK(cudaStreamWaitEvent(ln->L[i], ln->evStart, 0));
+    if (int e = layer_over_lanes(ln, y, b, sigma, B, chunk, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap)) return e;
+    CK(cudaEventRecord(ln->evEnd, ln->L[0]));
+    CK(cudaStreamWaitEvent(cs, ln->evEnd, 0));
+    return 0;
+}
+
 extern "C" int admmnet_forward(const void* y, const void* b, const float* sigma, int B, int chunk, int Mdim, int Ndim,
                                int K, const float* params, void* phi_out, void* ws, size_t ws_bytes, int rcap,
                                void* stream) {
@@ -526,40 +592,22 @@ extern "C" int admmnet_forward(const void* y, const void* b, const float* sigma,
     if (int e = check_net_args(B, chunk, n, K, rcap)) return e;
     cudaStream_t cs = (cudaStream_t)stream;
     if (int e = admmnet_reset_status(ws, ws_bytes, B, chunk, n, K, rcap, stream)) return e;
-    static const bool use_lanes = !(getenv("ADMMNET_LANES") && atoi(getenv("ADMMNET_LANES")) == 0);
-    if (!use_lanes) {      // single-stream variant (profiling): every launch on the caller's stream
+    if (!lanes_enabled()) {      // single-stream variant (profiling): every launch on the caller's stream
         for (int k = 0; k < K - 1; ++k) {
-            for (int off = 0; off < B; off += chunk) {
-                const int Bc = B - off < chunk ? B - off : chunk;
-                if (int e = admmnet_layer_chunk(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes,
-                                                rcap, stream))
-                    return e;
-            }
-            if (int e = admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, stream)) return e;
+            if (int e = admmnet_layer(y, b, sigma, B, chunk, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap, stream))
+                return e;
             if (int e = admmnet_set_mean(ws, ws_bytes, B, chunk, n, K, rcap, k, (double)B, stream)) return e;
         }
         return admmnet_final_phi(y, b, B, chunk, Mdim, Ndim, K, params, phi_out, ws, ws_bytes, rcap, stream);
     }
     Lanes* ln = nullptr;
-    if (int e = get_lanes(&ln)) return e;
+    if (int e = get_lanes(cs, &ln)) return e;
     // fork: the lanes start after everything already queued on the caller's stream
     CK(cudaEventRecord(ln->evStart, cs));
     for (int i = 0; i < NSLOT; ++i) CK(cudaStreamWaitEvent(ln->L[i], ln->evStart, 0));
     for (int k = 0; k < K - 1; ++k) {
-        int c = 0;
-        for (int off = 0; off < B; off += chunk, ++c) {
-            const int Bc = B - off < chunk ? B - off : chunk;
-            const int s = c % NSLOT;
-            if (int e = layer_chunk_impl(y, b, sigma, B, chunk, off, Bc, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap,
-                                         ln->L[s], s, ln->Q[s], ln->evH[s], ln->evQ[s]))
-                return e;
-        }
-        // join the lanes on lane 0, reduce the residual norms there, release the other lanes
-        for (int i = 1; i < NSLOT; ++i) {
-            CK(cudaEventRecord(ln->evDone[i], ln->L[i]));
-            CK(cudaStreamWaitEvent(ln->L[0], ln->evDone[i], 0));
-        }
-        if (int e = admmnet_layer_rsum(ws, ws_bytes, B, chunk, n, K, rcap, k, ln->L[0])) return e;
+        if (int e = layer_over_lanes(ln, y, b, sigma, B, chunk, Mdim, Ndim, K, k, params, ws, ws_bytes, rcap)) return e;
+        // the mean is finalised on lane 0; release the other lanes
         if (int e = admmnet_set_mean(ws, ws_bytes, B, chunk, n, K, rcap, k, (double)B, ln->L[0])) return e;
         CK(cudaEventRecord(ln->evMean, ln->L[0]));
         for (int i = 1; i < NSLOT; ++i) CK(cudaStreamWaitEvent(ln->L[i], ln->evMean, 0));
@@ -639,14 +687,21 @@ extern "C" int admm_classic_forward(const void* y, const void* b, int in_is_c128
     if (B <= 0 || n <= 0 || n > 256 || n_iter < 0) return fail(ADMMNET_ERR_ARG, "need B > 0, 0 < n <= 256, n_iter >= 0");
     cudaStream_t st = (cudaStream_t)stream;
     prof::Scope pscope(prof::CLASSIC, st);
-    const int grid = (int)(((long long)B * 32 + 255) / 256);      // one warp per signal
-    if (n <= 128) {
-        if (in_is_c128) k_classic<double2, 4, 32><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
-        else k_classic<float2, 4, 32><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
+    static const int gl_env = getenv("ADMMNET_CLASSIC_GL") ? atoi(getenv("ADMMNET_CLASSIC_GL")) : 0;
+    const int gl = (gl_env == 8 && n <= 104) ? 8 : (gl_env == 16 && n <= 112) ? 16 : (gl_env == 32) ? 32
+                   : (n <= 104 ? 8 : 32);
+    const int grid = (int)(((long long)B * gl + 255) / 256);      // one group of gl lanes per signal
+#define CLASSIC_LAUNCH(T, E, G) k_classic<T, E, G><<<grid, 256, 0, st>>>((const T*)y, (const T*)b, B, n, rho, n_iter, (double2*)phi_out)
+    if (gl == 8) {
+        if (in_is_c128) CLASSIC_LAUNCH(double2, 13, 8); else CLASSIC_LAUNCH(float2, 13, 8);
+    } else if (gl == 16) {
+        if (in_is_c128) CLASSIC_LAUNCH(double2, 7, 16); else CLASSIC_LAUNCH(float2, 7, 16);
+    } else if (n <= 128) {
+        if (in_is_c128) CLASSIC_LAUNCH(double2, 4, 32); else CLASSIC_LAUNCH(float2, 4, 32);
     } else {
-        if (in_is_c128) k_classic<double2, 8, 32><<<grid, 256, 0, st>>>((const double2*)y, (const double2*)b, B, n, rho, n_iter, (double2*)phi_out);
-        else k_classic<float2, 8, 32><<<grid, 256, 0, st>>>((const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);
+        if (in_is_c128) CLASSIC_LAUNCH(double2, 8, 32); else CLASSIC_LAUNCH(float2, 8, 32);
     }
+#undef CLASSIC_LAUNCH
     CK(cudaGetLastError());
     return 0;
 }
@@ -691,6 +746,29 @@ extern "C" int peak_search_points(const void* phi, int phi_is_c128, int xbase, i
         return fail(ADMMNET_ERR_ARG, "xbase/ybase must be in [1,32]");
     const size_t sm = (size_t)xbase * ybase * sizeof(double2);
     k_peak_points<<<(npts + 255) / 256, 256, sm, (cudaStream_t)stream>>>(phi, phi_is_c128, xbase, ybase, X, Y, npts, out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ tcgen05 / TMEM / TMA probe
+extern "C" int admmnet_tc_gemm_probe(const float* A, const float* B, const float* D0, int N, int K, int flags,
+                                     float* out, void* stream) {
+    if (!A || !B || !out) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (N < 8 || N > 256 || (N % 8) || K < 8 || K > 64 || (K % 8)) return fail(ADMMNET_ERR_ARG, "need N in [8,256] step 8, K in [8,64] step 8");
+    if ((flags & TCP_A_TMEM) && (flags & TCP_A_MN)) return fail(ADMMNET_ERR_ARG, "A in TMEM has no major-ness");
+    const size_t sm = 1024 + (size_t)(3 * 128 + 3 * N) * K * sizeof(float);
+    if (sm > 227 * 1024) return fail(ADMMNET_ERR_ARG, "probe tile does not fit shared memory");
+    TcProbeArgs a;
+    a.A = A; a.B = B; a.D0 = D0; a.out = out; a.N = N; a.K = K; a.flags = flags;
+    CUtensorMap tmA, tmB;
+    memset(&tmA, 0, sizeof(tmA));
+    memset(&tmB, 0, sizeof(tmB));
+    if (flags & TCP_TMA) {
+        if (!make_tmap_2d_f32(&tmA, A, 128, K, (uint64_t)K * 4, 128, K) || !make_tmap_2d_f32(&tmB, B, N, K, (uint64_t)K * 4, N, K))
+            return fail(ADMMNET_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    }
+    CK(cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_tc_probe<<<1, 128, sm, (cudaStream_t)stream>>>(a, tmA, tmB);
     CK(cudaGetLastError());
     return 0;
 }

@@ -18,7 +18,7 @@ __device__ __forceinline__ double2 ld_c<float2>(const float2* p, size_t i) {
     return make_double2((double)v.x, (double)v.y);
 }
 
-// One signal per group of GL lanes (GL = 32 in use; GL = 16 with 8 elements per lane measured 10 % slower).
+// One signal per group of GL lanes (ADMMNET_CLASSIC_GL = 8 | 16 | 32 selects; see the instantiations below).
 // MAXE: elements per lane (n <= GL*MAXE).
 template <typename CIn, int MAXE, int GL>
 __global__ void __launch_bounds__(256)
@@ -82,5 +82,12 @@ template __global__ void k_classic<double2, 4, 32>(const double2*, const double2
 template __global__ void k_classic<float2, 4, 32>(const float2*, const float2*, int, int, double, int, double2*);
 template __global__ void k_classic<double2, 8, 32>(const double2*, const double2*, int, int, double, int, double2*);
 template __global__ void k_classic<float2, 8, 32>(const float2*, const float2*, int, int, double, int, double2*);
+// 8 lanes per signal (13 elements per lane, n <= 104): the per-iteration reduction is 3 shuffle steps shared by the
+// 4 signals of a warp instead of 5 steps for one — the shuffle pipe (one warp instruction per clock per SM), not HBM,
+// bounded the 32-lane form at n_iter = 5.
+template __global__ void k_classic<double2, 13, 8>(const double2*, const double2*, int, int, double, int, double2*);
+template __global__ void k_classic<float2, 13, 8>(const float2*, const float2*, int, int, double, int, double2*);
+template __global__ void k_classic<double2, 7, 16>(const double2*, const double2*, int, int, double, int, double2*);
+template __global__ void k_classic<float2, 7, 16>(const float2*, const float2*, int, int, double, int, double2*);
 
 }  // namespace admmnet

@@ -9,7 +9,7 @@ shards, weights replicated.  The only cross-signal coupling of the reference is 
                         and the next layer's dual update.
 
 `run_layers` is engine-agnostic so the orchestration is testable on CPU (gloo) with a stand-in engine;
-`CudaEngine` drives the split-phase C ABI (admmnet_layer_chunk / _layer_rsum / _set_mean / _final_phi).
+`CudaEngine` drives the split-phase C ABI (admmnet_layer / _set_mean / _final_phi).
 """
 import ctypes as C
 
@@ -76,14 +76,13 @@ class CudaEngine:
                                                 self._stream()))
 
     def layer(self, k):
+        # all chunks over the library's chunk lanes, joined back into the current stream, then the residual-norm sum:
+        # everything stream-ordered, so the all-reduce that follows needs no host synchronisation
         m, ws = self.m, self.ws
-        for off in range(0, self.B, self.chunk):
-            Bc = min(self.chunk, self.B - off)
-            _capi.check(self.L.admmnet_layer_chunk(self.y.data_ptr(), self.b.data_ptr(), self.sigma.data_ptr(), self.B,
-                                                   self.chunk, off, Bc, m.M, m.N, m.num_layers, k, self.P.data_ptr(),
-                                                   ws.ptr, ws.nbytes, m.rcap, self._stream()))
-        _capi.check(self.L.admmnet_layer_rsum(ws.ptr, ws.nbytes, self.B, self.chunk, m.M * m.N, m.num_layers, m.rcap,
-                                              k, self._stream()))
+        with torch.cuda.device(self.dev):
+            _capi.check(self.L.admmnet_layer(self.y.data_ptr(), self.b.data_ptr(), self.sigma.data_ptr(), self.B,
+                                             self.chunk, m.M, m.N, m.num_layers, k, self.P.data_ptr(), ws.ptr,
+                                             ws.nbytes, m.rcap, self._stream()))
 
     def rsum(self, k):
         return self.ws.rsum[k:k + 1]

@@ -6,30 +6,44 @@ import torch
 import torch.distributed as dist
 
 
-def allreduce_gradients(model, group=None):
-    """Average .grad over the ranks with ONE all-reduce of a flat fp32 buffer (132 230 floats = 0.53 MB at K=10)."""
+def allreduce_gradients(model, group=None, weight=1.0):
+    """Average .grad over the ranks with ONE all-reduce of a flat fp32 buffer (132 230 floats = 0.53 MB at K=10).
+    `weight` = this rank's number of samples in the global batch: the result is the sample-weighted mean
+    sum_r w_r g_r / sum_r w_r, i.e. the mean gradient of the global batch even when the shards are ragged; a rank
+    whose shard is empty passes weight 0 (its gradients count as zeros) and still takes part in the collective."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     params = [p for p in model.parameters() if p.requires_grad]
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    w = torch.tensor([float(weight)], device=params[0].device, dtype=torch.float32)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() * w
+                      for p in params] + [w])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat /= dist.get_world_size(group)
+    flat = flat[:-1] / flat[-1].clamp(min=1e-30)
     off = 0
     for p in params:
         nel = p.numel()
         if p.grad is not None:
             p.grad.copy_(flat[off:off + nel].view_as(p))
+        elif weight == 0:
+            p.grad = flat[off:off + nel].view_as(p).clone()
         off += nel
 
 
 def train_step(model, criterion, optimizer, y, b, sigma, phi_true, max_norm=1.0, group=None):
-    """optimizer.zero_grad -> forward -> loss -> backward -> all-reduce -> clip -> step  (trainPhi.py:165-178)."""
+    """optimizer.zero_grad -> forward -> loss -> backward -> all-reduce -> clip -> step  (trainPhi.py:165-178).
+    A rank with an empty shard (y.shape[0] == 0: tail batch smaller than the world size) skips forward/backward but
+    still joins the all-reduce with weight 0 and applies the same optimizer step, so the replicas stay in sync."""
     model.train()
     optimizer.zero_grad()
-    phi = model(y, b, sigma)
-    loss, parts = criterion(phi, phi_true)
-    loss.backward()
-    allreduce_gradients(model, group)
+    nloc = y.shape[0]
+    if nloc > 0:
+        phi = model(y, b, sigma)
+        loss, parts = criterion(phi, phi_true)
+        loss.backward()
+    else:
+        dev = next(model.parameters()).device
+        loss, parts = torch.zeros((), device=dev), {}
+    allreduce_gradients(model, group, weight=nloc)
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
     optimizer.step()
     return loss.detach(), parts
@@ -53,8 +67,7 @@ def _batches(tensors, batch_size, order, rank, world):
     for lo in range(0, n, batch_size):
         idx = order[lo:min(lo + batch_size, n)]
         a, b = shard_range(idx.numel(), rank, world)
-        if b > a:
-            yield tuple(t[idx[a:b]] for t in tensors)
+        yield tuple(t[idx[a:b]] for t in tensors)      # possibly empty: every rank yields the same number of steps
 
 
 def fit(model, train, val, config, device="cuda", group=None, log=print):
@@ -85,13 +98,16 @@ def fit(model, train, val, config, device="cuda", group=None, log=print):
         for y, b, s, pt in _batches(sel(train), bs, order, rank, world):
             y, b, s, pt = (t.to(device, non_blocking=True) for t in (y, b, s, pt))
             loss, _ = train_step(model, criterion, optimizer, y, b, s, pt, group=group)
-            tot += loss
-            nb += 1
+            if y.shape[0]:
+                tot += loss
+                nb += 1
         train_loss = float(tot) / max(nb, 1)
         model.eval()
         vt, vb = torch.zeros((), device=device), 0
         with torch.no_grad():
             for y, b, s, pt in _batches(sel(val), bs, torch.arange(val[0].shape[0]), rank, world):
+                if y.shape[0] == 0:
+                    continue
                 y, b, s, pt = (t.to(device, non_blocking=True) for t in (y, b, s, pt))
                 vt += criterion(model(y, b, s), pt)[0]
                 vb += 1

@@ -6,11 +6,14 @@ forward + peak search at 1/2/4/8 B200, % of roofline, reference CPU path beside 
     python bench.py --impl reference --gpus N ...            # the reference's algorithm on the host cores
 
 Workload (config.workload): BASELINE.json configs[2] — ADMM-Net K=10, n = 10x10, forward + alt_peak_search
-(99x99 coarse grid, iter=3, top-3), synthetic signals of generate_data.py's recipe.  Weak scaling: every
-rank processes --per-gpu signals per step (default 131072 = the per-GPU share of the 1M batch at 8 GPUs),
-so at N=8 one step IS the 1M-signal configuration.  No collective on the data path (norm_scope='shard':
-the ZLayer batch mean is taken over each rank's shard; --norm-scope global adds 9 scalar all-reduces).
-One step = one pass over the batch; timed with CUDA events between barriers, max over ranks.
+(99x99 coarse grid, iter=3, top-3), a batch of --signals = 1 048 576 synthetic signals of generate_data.py's
+recipe, sharded over the N ranks (strong scaling: N=1 processes the whole 1M batch on one B200, 87 GB of
+per-signal state).  --per-gpu overrides the shard size (development runs; then the line says "weak").
+No collective on the data path (norm_scope='shard': the ZLayer batch mean is taken over each rank's shard);
+the exact whole-batch semantics (--norm-scope global: 9 scalar all-reduces per forward) is timed and checked
+as extras.global_scope whenever N > 1.  One step = one pass over the batch; timed with CUDA events between
+barriers, max over ranks.  After the timed region a random subset of the batch is recomputed with the CPU
+oracle (per-layer batch means read back from the device) and compared: the `parity` object of the JSON line.
 """
 import argparse
 import ctypes as C
@@ -140,11 +143,74 @@ def run_reference(args):
               "signals/s = 1/(t_fwd/n_fwd + t_peak/n_peak)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "signals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
+            "higher_is_better": True, "scaling": "weak" if args.per_gpu else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": "signals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "signals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def torch_cuda_baseline(dev, B=4096, reps=2):
+    """BASELINE.md §3.4 "the GPU bar to beat": the reference's own op sequence (oracle port of
+    PhiEstADMMNet.forward: torch.linalg.eigh -> cuSOLVER, bmm -> cuBLAS, ~150 torch ops per layer) with all
+    tensors on the B200, no_grad.  /root/reference does not exist on the GPU box, so the op-for-op port is what
+    runs; it is pinned to the reference by tests/golden."""
+    from oracle import net_oracle
+    import admmnet_b200
+    torch.manual_seed(0)
+    sd = admmnet_b200.PhiEstADMMNet(M, N, 3, K_LAYERS).state_dict()
+    y, b, s = tile_signals(B, seed=55)
+    yt, bt, st = (torch.from_numpy(a).to(dev) for a in (y, b, s))
+    net_oracle.forward(sd, yt[:256], bt[:256], st[:256], M, N, K_LAYERS)        # warm-up (cuSOLVER handles)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        net_oracle.forward(sd, yt, bt, st, M, N, K_LAYERS)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return {"value": B / (best * 1e-3), "unit": "signals/s (forward only, no peak search)", "batch": B, "ms": best,
+            "what": "oracle port of the reference forward as stock PyTorch CUDA ops on this B200 "
+                    "(torch.linalg.eigh/cuSOLVER + cuBLAS bmm + elementwise), no_grad, best of %d" % reps}
+
+
+def run_torch_cuda(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    g = torch_cuda_baseline(dev)
+    print(json.dumps({"impl": "torch-cuda", "metric": METRIC + " (forward only)", "value": g["value"],
+                      "unit": "signals/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "gpu_baseline": g}))
+
+
+def parity_check(model, yd, bd, sd_, phi_dev, top_dev, means, n_fwd=64, n_peak=8, seed=7):
+    """Recompute a random subset of the batch the timed steps processed with the CPU oracle and compare.
+    The ZLayer batch mean couples the signals (admm_net.py:459), so the oracle gets the per-layer means the device
+    used (ws.mean, read back) — then each signal's result only depends on its own data.  Peak search: the oracle's
+    alt_peak_search (separable surface) on the SAME phi the device search saw, top-L positions must be bit-equal."""
+    from oracle import net_oracle, peak_oracle
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randperm(yd.shape[0], generator=g)[:n_fwd].sort().values
+    idd = idx.to(yd.device)
+    yt, bt, st = yd[idd].cpu(), bd[idd].cpu(), sd_[idd].cpu()
+    ref = net_oracle.forward(model.state_dict(), yt, bt, st, M, N, K_LAYERS, means=means)
+    got = phi_dev[idd].cpu()
+    rel = ((got - ref).abs().amax(1) / ref.abs().amax(1))
+    top = top_dev[idd[:n_peak]].cpu().numpy()
+    same = True
+    for i in range(n_peak):
+        r = peak_oracle.alt_peak_search({"phi": got[i].numpy(), "xbase": N, "ybase": M}, PEAK_OPTS,
+                                        surface=lambda p, X, xb, Y, yb: peak_oracle.peak_search_separable(p, X[0], xb, Y[:, 0], yb))
+        t = peak_oracle.top_l(r, TOPL)
+        same = same and np.array_equal(np.asarray(t)[:, :2], top[i][:len(t), :2])
+    return {"signals_checked": int(n_fwd), "phi_rel_max": float(rel.max()), "phi_rel_median": float(rel.median()),
+            "peaks_checked": int(n_peak), "peaks_identical": bool(same), "tolerance": 1e-4,
+            "how": "CPU oracle on a random subset of the timed batch with the device's per-layer batch means"}
 
 
 def _time_ms(fn, reps):
@@ -179,35 +245,64 @@ def measure_extras(pkg, dev):
         out[f"latency_b1_k{K}_ms"] = float(np.median(ts))
     out["latency_published_ms"] = {"k10_mean": 191.0, "k5_mean": 96.5, "classic_mean": 524.4,
                                    "source": "results/time/time_net.txt, time_net_5.txt, time.txt (hardware not stated)"}
-    # configs[1]: classical ADMM, batch 65536, complex64 inputs -> complex128 phi, 5 iterations (what admm_for_us executes)
+    # configs[1]: classical ADMM, batch 65536, complex64 inputs -> complex128 phi; n_iter = 5 (what admm_for_us
+    # executes) and 100 (SURVEY.md §8d cfg 2).  HBM-bound: roofline-style entries against the measured copy bandwidth.
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     Bc = 65536
     y, b, s = tile_signals(Bc, seed=77)
     yd, bd = torch.from_numpy(y).to(dev), torch.from_numpy(b).to(dev)
     o = torch.empty(Bc, M * N, dtype=torch.complex128, device=dev)
-    pkg.admm_for_us_batched(yd, bd, 1.0, 5, out=o)
-    ms = _time_ms(lambda: pkg.admm_for_us_batched(yd, bd, 1.0, 5, out=o), 20)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # 256 MB > 126 MB L2
     byt = Bc * (800 + 800 + 1600)
-    out["classic_64k"] = {"signals_per_s": Bc / (ms * 1e-3), "ms": ms, "algorithmic_bytes": byt,
-                          "achieved_gbs": byt / (ms * 1e-3) / 1e9,
-                          "note": "c64 y,b in / c128 phi out = 3204 B per signal; working set 210 MB > 126 MB L2"}
-    # configs[3]: peak-search steering-dictionary sweep (n x grid), batch 8192 per point
+    for it in (5, 100):
+        pkg.admm_for_us_batched(yd, bd, 1.0, it, out=o)
+        ts = []
+        for _ in range(10):
+            flush.zero_()                                                  # L2 flush between timed iterations
+            ts.append(_time_ms(lambda: pkg.admm_for_us_batched(yd, bd, 1.0, it, out=o), 1))
+        ms = float(np.median(ts))
+        out[f"classic_64k_iter{it}"] = {
+            "signals_per_s": Bc / (ms * 1e-3), "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": byt / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": byt / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": byt,
+                         "peak_source": "measured" if peaks else "fallback"},
+            "note": "BASELINE.json configs[1]; c64 y,b in / c128 phi out = 3204 B per signal, 210 MB per launch; "
+                    "L2 flushed (256 MB memset) before every timed launch, median of 10"}
+    del flush
+    # stock PyTorch CUDA ops of the reference forward on this B200
+    out["gpu_baseline"] = torch_cuda_baseline(dev)
+    # configs[3]: peak-search steering-dictionary sweep (n x grid), batch 262144 per point
     sweep = []
     rng = np.random.default_rng(3)
-    for nb, g in ((8, 32), (10, 45), (12, 64), (16, 64)):
-        Bp = 8192
-        phi = torch.from_numpy((rng.normal(size=(Bp, nb * nb)) + 1j * rng.normal(size=(Bp, nb * nb))).astype(np.complex64)).to(dev)
+    Bp = 262144
+    for nb, g in ((8, 32), (10, 45), (12, 64), (14, 64), (16, 64)):
+        base = torch.from_numpy((rng.normal(size=(4096, nb * nb)) + 1j * rng.normal(size=(4096, nb * nb))).astype(np.complex64)).to(dev)
+        ph = torch.exp(1j * torch.rand(Bp // 4096, 1, 1, device=dev) * 6.2831853).to(torch.complex64)
+        phi = (base[None] * ph).reshape(Bp, nb * nb).contiguous()
         opts = dict(xstep=1.0 / g, ystep=1.0 / g, iter=3)
-        pkg.alt_peak_search_batched(phi, nb, nb, opts, topl=3, pmax=512)
-        ms = _time_ms(lambda: pkg.alt_peak_search_batched(phi, nb, nb, opts, topl=3, pmax=512), 3)
-        sweep.append({"n": nb * nb, "grid": f"{g - 1}x{g - 1}", "signals_per_s": Bp / (ms * 1e-3)})
+        pkg.alt_peak_search_batched(phi, nb, nb, opts, topl=3, pmax=256)
+        ms = _time_ms(lambda: pkg.alt_peak_search_batched(phi, nb, nb, opts, topl=3, pmax=256), 1)
+        flop = 8.0 * ((g - 1) * nb * nb + (g - 1) * nb * (g - 1))          # separable coarse surface, SURVEY §8d
+        sweep.append({"n": nb * nb, "grid": f"{g - 1}x{g - 1}", "batch": Bp, "signals_per_s": Bp / (ms * 1e-3),
+                      "ms": ms, "coarse_surface_gflops": flop * Bp / (ms * 1e-3) / 1e9})
+        del phi
     out["peak_search_sweep"] = sweep
     return out
 
 
-def workload_config(args):
+def workload_config(args, world=None):
+    world = world or args.gpus
+    per = args.per_gpu if args.per_gpu else args.signals // world
+    how = (f"{per} signals per GPU per step (--per-gpu override), weak scaling" if args.per_gpu else
+           f"{args.signals} signals per step sharded over {world} GPU(s) = {per} per GPU, strong scaling")
     return {"workload": f"BASELINE.json configs[2]: ADMM-Net K={K_LAYERS}, n={M}x{N}, forward + alt_peak_search "
-                        f"(99x99, iter=3, top-{TOPL}); {args.per_gpu} signals per GPU per step (1M/8), weak scaling",
-            "per_gpu_batch": args.per_gpu, "chunk": args.chunk, "norm_scope": args.norm_scope,
+                        f"(99x99, iter=3, top-{TOPL}); {how}",
+            "signals_per_step": per * world, "per_gpu_batch": per, "chunk": args.chunk, "norm_scope": args.norm_scope,
             "l2": "working set per step (>10 GB of per-signal state) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -216,15 +311,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--per-gpu", type=int, default=131072)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-cuda"])
+    ap.add_argument("--signals", type=int, default=1048576, help="batch per step, sharded over the ranks")
+    ap.add_argument("--per-gpu", type=int, default=0, help="override: signals per GPU per step (weak scaling)")
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--norm-scope", default="shard", choices=["shard", "global"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "torch-cuda":
+        return run_torch_cuda(args)
 
     import admmnet_b200
     from admmnet_b200 import _capi, sharding
@@ -240,7 +339,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
 
-    B = args.per_gpu
+    B = args.per_gpu if args.per_gpu else args.signals // world
     torch.manual_seed(0)
     model = admmnet_b200.PhiEstADMMNet(M, N, 3, K_LAYERS).eval()
     model.chunk = args.chunk
@@ -303,11 +402,44 @@ def main():
     _capi.check(L.admmnet_status(ws.ptr, ws.nbytes, ws.B, ws.chunk, ws.n, ws.K, ws.rcap,
                                  torch.cuda.current_stream().cuda_stream, C.byref(st)))
     assert st.value == 0, f"eigen-solver status {st.value}"
+    # parity of the benchmarked configuration itself (rank 0): the last timed step's outputs against the CPU oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        phi_last, pk_last = step_device(yd, bd, sd_)
+        means = ws.mean[:K_LAYERS - 1].cpu().tolist()
+        parity = parity_check(model, yd, bd, sd_, phi_last, pk_last["top"], means)
+        assert parity["phi_rel_max"] < 1e-4, parity
+        assert parity["peaks_identical"], parity
+        del phi_last, pk_last
 
     # end-to-end through the public API with host buffers
     step_e2e()
     ms_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
     e2e_steps = max(1, min(args.steps, 3))
+
+    # exact whole-batch semantics across the ranks (SURVEY.md §8e 'global'): 9 scalar all-reduces per forward
+    global_scope = None
+    if world > 1 and not args.no_extras:
+        def step_global():
+            phi = sharding.sharded_forward(model, yd, bd, sd_, "global")
+            return phi, admmnet_b200.alt_peak_search_batched(phi, N, M, PEAK_OPTS, topl=TOPL, pmax=256)
+        step_global()
+        ms_g = timed(step_global, 1)
+        # parity against ONE GPU computing the whole (small) batch: every rank takes 4096 signals of a 4096*world
+        # batch generated from one seed; rank 0 also runs all of it alone with norm_scope='batch'
+        Bs = 4096
+        ya, ba, sa = admmnet_b200.generate_signals(Bs * world, M, N, 3, snr_w=20.0, snr_demod=7.0, seed=4321, device=dev)
+        lo = rank * Bs
+        phi_g = sharding.sharded_forward(model, ya[lo:lo + Bs], ba[lo:lo + Bs], sa[lo:lo + Bs], "global")
+        par = None
+        if rank == 0:
+            phi_1 = model.forward_device(ya, ba, sa)[:Bs]
+            par = float(((phi_g - phi_1).abs().amax(1) / phi_1.abs().amax(1)).max().item())
+        global_scope = {"value": world * B / (ms_g * 1e-3), "unit": "signals/s", "ms_per_step": ms_g,
+                        "parity_vs_single_gpu": par, "collectives_per_step": K_LAYERS - 1,
+                        "note": "norm_scope=global: chunk lanes kept (admmnet_layer), one fp64 NCCL all-reduce per "
+                                "active layer, stream-ordered (no host sync); parity = max rel. difference of rank 0's "
+                                "shard against one GPU running the whole 4096*N batch"}
 
     # FP32 FMA peak (roofline denominator), timed alone
     outp = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
@@ -329,7 +461,18 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    # TF32 tensor-pipe peak (SURVEY.md §8d asks for both denominators): cuBLAS 8192^3 with TF32 allowed, best of 5
+    torch.backends.cuda.matmul.allow_tf32 = True
+    am = torch.randn(8192, 8192, device=dev)
+    bm = torch.randn(8192, 8192, device=dev)
+    torch.matmul(am, bm)
+    tf32_best = min(_time_ms(lambda: torch.matmul(am, bm), 1) for _ in range(5))
+    tf32_peak_tflops = 2 * 8192 ** 3 / (tf32_best * 1e-3) / 1e12
+    torch.backends.cuda.matmul.allow_tf32 = False
+    del am, bm
     extras = None if args.no_extras else measure_extras(admmnet_b200, dev)
+    if extras is not None and global_scope is not None:
+        extras["global_scope"] = global_scope
     names = [L.admmnet_profile_kind_name(i).decode() for i in range(nk)]
     kern = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kln[i] / args.steps} for i in range(nk) if kln[i]}
     gpu_ms = sum(v["ms_per_step"] for v in kern.values())
@@ -353,13 +496,19 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     line = {
         "metric": METRIC, "value": value, "unit": "signals/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak" if args.per_gpu else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e / e2e_steps * 1e-3), "unit": "signals/s",
                 "h2d_bytes_per_step": int(yh.nbytes + bh.nbytes + sh.nbytes),
                 "d2h_bytes_per_step": int(phi_h.nbytes + top_h.nbytes + cnt_h.nbytes)},
         "gpu_launches": int(sum(kln[i] for i in range(nk))),
+        "parity": parity,
+        "peaks": {"fp32_fma_tflops": fp32_peak_tflops, "tf32_tensor_tflops": tf32_peak_tflops,
+                  "bf16_tensor_tflops": peaks.get("bf16_tflops"), "hbm_gbs": hbm_peak,
+                  "how": "FP32: FFMA micro-kernel in this library; TF32: torch.matmul 8192^3 allow_tf32, best of 5; "
+                         "bf16 and HBM: MEASURED_PEAKS.json"},
         "roofline": {
             "bound": "fp32", "kernel": "layer pipeline k_head+k_head2+k_ql+k_rot+k_tail (dominant: %s)" % dom,
             "forward_ms_per_step": fwd_ms,

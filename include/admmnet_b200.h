@@ -13,8 +13,10 @@
  *   - work is ordered after everything queued on the caller's stream (cudaStream_t passed as void*)
  *     and the stream waits for it; admmnet_forward additionally fans chunks out over library-owned
  *     non-blocking streams (two chunk lanes + a high-priority lane for the latency-bound QL kernel)
- *     between a fork and a join event.  Calls are re-entrant across streams given distinct
- *     workspaces.  No C++ exception crosses the ABI.
+ *     between a fork and a join event.  Those streams and events are kept per (device, caller stream), so calls
+ *     are re-entrant across host threads and streams given distinct workspaces and distinct streams
+ *     (tests/test_gpu_parity.py::test_forward_is_reentrant_across_host_threads_and_streams).  The device that
+ *     owns the buffers must be current (cudaSetDevice) when calling.  No C++ exception crosses the ABI.
  *   - complex64 = interleaved float pairs, complex128 = interleaved double pairs, row-major.
  */
 #ifndef ADMMNET_B200_H
@@ -69,6 +71,11 @@ int admmnet_layer_chunk(const void* y, const void* b, const float* sigma, int B,
                         int Mdim, int Ndim, int K, int k, const float* params, void* ws, size_t ws_bytes, int rcap,
                         void* stream);
 int admmnet_layer_rsum(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k, void* stream);
+/* One whole layer of the local batch the way admmnet_forward runs it: all chunks fanned out over the chunk lanes
+ * (forked from and joined back into `stream`), followed by admmnet_layer_rsum(k).  The multi-GPU 'global' norm scope
+ * (sharding.py) calls this, all-reduces rsum[k] on `stream`, then admmnet_set_mean — no host synchronisation.  */
+int admmnet_layer(const void* y, const void* b, const float* sigma, int B, int chunk, int Mdim, int Ndim, int K, int k,
+                  const float* params, void* ws, size_t ws_bytes, int rcap, void* stream);
 int admmnet_ws_scalars(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, double** rsum,
                        float** mean, int** status);
 int admmnet_set_mean(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, int k, double count,
@@ -161,6 +168,15 @@ int admmnet_profile_kinds(void);
 const char* admmnet_profile_kind_name(int kind);
 int admmnet_profile_end(double* ms, long long* launches);
 int admmnet_fp32_peak_launch(float* out, int grid, int iters, double* flops, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Debug tap of the tcgen05 / TMEM / TMA layer (csrc/tc.cuh) the tail kernel is built on: one 128 x N x K tf32 tile,
+ * out = D0 + (+-A) * B^T, A [128][K], B [N][K], D0/out [128][N] row-major fp32 on the device.
+ * flags: 1 A from tensor memory, 2 negate A, 4 A staged MN-major, 8 B staged MN-major, 16 operands loaded by TMA,
+ * 32 3xTF32 split (arbitrary fp32 inputs, fp32-class result).  No reference counterpart (unit test of the machinery).
+ * ------------------------------------------------------------------------------------------- */
+int admmnet_tc_gemm_probe(const float* A, const float* B, const float* D0, int N, int K, int flags, float* out,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,7 @@ def h_update(G, Z, sigma, n, p):
     rho = _sp(p["rho"])
     T = G[:, :n, :n] + Z[:, :n, :n] / (rho + EPS)
     t = torch.diagonal(T, dim1=1, dim2=2).real
-    A = 2 * torch.sqrt(torch.tensor(n).float()) * sigma + sigma ** 2
+    A = 2 * torch.sqrt(torch.tensor(n).float()).to(sigma.device) * sigma + sigma ** 2
     A = A.view(-1, 1)
     corr = torch.tanh(F.linear(F.relu(F.linear(t, p["W1"], p["b1"])), p["W2"], p["b2"]))
     tc = t + 0.1 * corr
@@ -66,8 +66,8 @@ def h_update(G, Z, sigma, n, p):
 def block_matrix(phi, h, c):
     """[[diag(h), phi],[phi^H, c]] as complex64 (admm_net.py:273-284, 428-439)."""
     B, n = phi.shape
-    M = torch.zeros(B, n + 1, n + 1, dtype=torch.complex64)
-    idx = torch.arange(n)
+    M = torch.zeros(B, n + 1, n + 1, dtype=torch.complex64, device=phi.device)
+    idx = torch.arange(n, device=phi.device)
     M[:, idx, idx] = h.to(torch.complex64)
     M[:, :n, n] = phi
     M[:, n, :n] = phi.conj()
@@ -110,8 +110,8 @@ def z_update(phi, h, G, Z, k, p, mean_r=None):
     rho = _sp(p["rho"])
     r = torch.norm(R, dim=[1, 2], p="fro")
     B = r.shape[0]
-    k_norm = torch.tensor(k / 10.0).repeat(B)
-    rho_norm = torch.full((B,), rho.item())
+    k_norm = torch.tensor(k / 10.0, device=r.device).repeat(B)
+    rho_norm = torch.full((B,), rho.item(), device=r.device)
     m = r.mean() if mean_r is None else mean_r
     res_norm = r / (m + EPS)
     feat = torch.stack([k_norm, rho_norm, res_norm], dim=1)
@@ -121,9 +121,9 @@ def z_update(phi, h, G, Z, k, p, mean_r=None):
     return Z + alpha.unsqueeze(-1).unsqueeze(-1) * R, r, alpha
 
 
-def layer_params(sd, k):
+def layer_params(sd, k, device=None):
     """Pick layer k's tensors out of a reference-format state_dict (keys: SURVEY.md §8a)."""
-    g = lambda name: sd[name].detach().float()
+    g = lambda name: sd[name].detach().float().to(device) if device is not None else sd[name].detach().float()
     return dict(
         phi=dict(rho=g(f"phiLayers.{k}.rho")),
         h=dict(rho=g(f"hLayers.{k}.rho"), projection_weight=g(f"hLayers.{k}.projection_weight"),
@@ -140,26 +140,29 @@ def layer_params(sd, k):
 
 
 @torch.no_grad()
-def forward(sd, y, b, sigma, M, N, num_layers, eigh=None, taps=None, chunk=None):
+def forward(sd, y, b, sigma, M, N, num_layers, eigh=None, taps=None, chunk=None, means=None):
     """PhiEstADMMNet.forward (admm_net.py:742-764).  y,b complex64 [B,n]; sigma fp32 [B] or [B,1].
 
     chunk: if given, the batch is processed in independent chunks of that many signals
-    (norm_scope='chunk' of the CUDA path: the ZLayer batch mean is taken per chunk)."""
+    (norm_scope='chunk' of the CUDA path: the ZLayer batch mean is taken per chunk).
+    means: optional per-layer values that replace the batch mean of admm_net.py:459 (used to check a SUBSET of a
+    large batch: the subset's signals then see the statistic of the batch they were computed in)."""
     if chunk is not None and y.shape[0] > chunk:
         outs = [forward(sd, y[i:i + chunk], b[i:i + chunk], sigma[i:i + chunk], M, N, num_layers, eigh)
                 for i in range(0, y.shape[0], chunk)]
         return torch.cat(outs, 0)
     n = M * N
     B = y.shape[0]
-    G = torch.zeros(B, n + 1, n + 1)
-    Z = torch.zeros(B, n + 1, n + 1)
+    G = torch.zeros(B, n + 1, n + 1, device=y.device)
+    Z = torch.zeros(B, n + 1, n + 1, device=y.device)
     phi = None
     for k in range(num_layers):
-        p = layer_params(sd, k)
+        p = layer_params(sd, k, y.device)
         phi = phi_update(y, b, G, Z, p["phi"]["rho"])
         h = h_update(G, Z, sigma, n, p["h"])
         G, Ah, vals, vc = g_update(phi, h, Z, p["g"], eigh)
-        Z, r, alpha = z_update(phi, h, G, Z, k, p["z"])
+        mr = None if means is None or k >= len(means) else torch.tensor(float(means[k]), dtype=torch.float32, device=y.device)
+        Z, r, alpha = z_update(phi, h, G, Z, k, p["z"], mean_r=mr)
         if taps is not None:
             taps.append(dict(phi=phi.clone(), h=h.clone(), A=Ah, vals=vals, vc=vc, G=G.clone(), r=r, alpha=alpha,
                              Z=Z.clone()))

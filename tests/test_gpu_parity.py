@@ -255,6 +255,71 @@ def test_ql_and_divide_and_conquer_paths_agree(pkg):
     assert rel_err(phi_dc, ref).max() < PHI_TOL
 
 
+def test_benchmarked_path_multichunk_lanes_against_oracle(pkg):
+    """the configuration bench.py times — several scratch chunks of MORE than 1024 signals
+    (plain-QL path, not divide & conquer), chunk lanes on, the persistent tail kernel on both scratch slots, whole-
+    batch norm scope — against the oracle run on the whole batch.  6000 signals = 3 chunks of 2000 over 2 lanes
+    (slot 0 twice, slot 1 once), perturbed weights, K = 10."""
+    from oracle import net_oracle, signals
+    z, sd = load_net_case("pert_k10")
+    net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
+    net.load_state_dict(sd)
+    y, b, s, _ = signals.generate(6000, seed=41)
+    yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
+    net.chunk = 2000
+    with torch.no_grad():
+        phi = net(yt.cuda(), bt.cuda(), st.cuda()).cpu().numpy()
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = net_oracle.forward(sd, yt, bt, st, 10, 10, 10).numpy()
+    err = rel_err(phi, ref)
+    assert err.max() < PHI_TOL, (err.max(), int(err.argmax()))
+    # ragged last chunk on the other slot: 4500 = 2000 + 2000 + 500 (the 500-signal launch takes the D&C path)
+    with torch.no_grad():
+        phi2 = net(yt[:4500].cuda(), bt[:4500].cuda(), st[:4500].cuda()).cpu().numpy()
+    ref2 = net_oracle.forward(sd, yt[:4500], bt[:4500], st[:4500], 10, 10, 10).numpy()
+    assert rel_err(phi2, ref2).max() < PHI_TOL
+
+
+def test_forward_is_reentrant_across_host_threads_and_streams(pkg):
+    """include/admmnet_b200.h: admmnet_forward is re-entrant across streams given distinct workspaces.  Two host
+    threads, two models (own workspaces), two CUDA streams, different inputs, run concurrently several times."""
+    import threading
+    from oracle import net_oracle, signals
+    z, sd = load_net_case("pert_k10")
+    data, refs, outs, errs = [], [], [None, None], []
+    for t in range(2):
+        y, b, s, _ = signals.generate(1500, seed=100 + t)
+        data.append(tuple(torch.from_numpy(a).cuda() for a in (y, b, s)))
+        refs.append(net_oracle.forward(sd, *(torch.from_numpy(a) for a in (y, b, s)), 10, 10, 10).numpy())
+    nets = []
+    for t in range(2):
+        net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
+        net.load_state_dict(sd)
+        net.chunk = 600                     # 3 chunks -> both lanes of each caller stream are busy
+        nets.append(net)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+
+    def work(t):
+        try:
+            with torch.cuda.stream(streams[t]), torch.no_grad():
+                for _ in range(3):
+                    out = nets[t].forward_device(*data[t])
+                streams[t].synchronize()
+            outs[t] = out.cpu().numpy()
+        except Exception as e:              # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for t in range(2):
+        assert rel_err(outs[t], refs[t]).max() < PHI_TOL
+
+
 def test_forward_other_shapes_and_edges(pkg):
     from oracle import net_oracle, signals
     torch.manual_seed(5)
@@ -311,6 +376,20 @@ def test_classic_matches_reference_golden_and_oracle(pkg):
         out = pkg.admm_for_us_batched(yt, bt, rho=0.7, n_iter=5).cpu().numpy()
         ref = classic_oracle.admm_linear_recursion(yt.cpu().numpy(), bt.cpu().numpy(), 0.7, 5)
         assert rel_err(out, ref).max() < 1e-12
+
+
+def test_classic_honours_zero_tolerances(pkg):
+    """admm.py:95-112 with eta_abs = eta_rel = 0 never stops early: max_iter iterations."""
+    from oracle import classic_oracle, signals
+    y, b, s, _ = signals.generate(1, seed=4)
+    opts = {"rho": 1.0, "max_iter": 9, "eta_abs": 0.0, "eta_rel": 0.0}
+    phi, it = pkg.admm_for_us(y[0], b[0], 10, 10, 0.1, float(s[0]), opts)
+    ref, it_ref = classic_oracle.admm_for_us(y[0].astype(np.complex128), b[0].astype(np.complex128), 10, 10, 0.1,
+                                             float(s[0]), opts)
+    assert it == it_ref == 9
+    assert np.abs(phi - ref).max() < 1e-12 * np.abs(ref).max()
+    phi5, it5 = pkg.admm_for_us(y[0], b[0], 10, 10, 0.1, float(s[0]), {"max_iter": 9})
+    assert it5 == 5
 
 
 def test_peak_search_matches_reference_golden(pkg):

@@ -109,3 +109,25 @@ def test_peak_oracle_matches_reference():
     ay = np.arange(-0.5, 0.5 - 0.01, 0.01)
     sep = peak_oracle.peak_search_separable(z["net0__phi"], ax, 10, ay, 10)
     np.testing.assert_allclose(sep, z["surface_net0"], rtol=1e-9, atol=1e-18)
+
+
+def test_classic_tolerances_of_zero_run_to_max_iter():
+    """with eta_abs = eta_rel = 0 the reference's loop (admm.py:95-112) never meets its stopping test and
+    runs max_iter iterations; the literal port shows it, the closed-form recursion agrees, and the product's
+    iteration rule (admm-net_b200/admm.py::executed_iterations) follows it."""
+    import importlib
+    from oracle import classic_oracle, signals
+    y, b, s, _ = signals.generate(1, seed=4)
+    y, b = y[0].astype(np.complex128), b[0].astype(np.complex128)
+    opts = {"rho": 1.0, "max_iter": 9, "eta_abs": 0.0, "eta_rel": 0.0}
+    phi, it = classic_oracle.admm_for_us(y, b, 10, 10, 0.1, float(s[0]), opts)
+    assert it == 9
+    rec = classic_oracle.admm_linear_recursion(y[None], b[None], 1.0, 9)[0]
+    assert np.abs(phi - rec).max() < 1e-12 * np.abs(rec).max()
+    rule = importlib.import_module("admmnet_b200.admm").executed_iterations
+    bn = float(np.sqrt(2 * np.sum(np.abs(phi) ** 2) + 1 / 0.1 ** 4))
+    assert rule(opts, True, 5, bn, 100) == 9
+    assert rule({"max_iter": 9}, True, 5, bn, 100) == 5
+    assert rule({"max_iter": 9}, False, 5, bn, 100) == 2
+    with pytest.raises(ValueError):
+        rule({"max_iter": 9, "eta_abs": 1e-16, "eta_rel": 0.0}, True, 5, bn, 100)

@@ -205,6 +205,68 @@ def test_batches_split_every_global_batch_over_the_ranks():
     order = torch.arange(10)
     got = [[t[0].tolist() for t in _batches((x,), 4, order, r, 2)] for r in range(2)]
     assert got[0] == [[0, 1], [4, 5], [8]] and got[1] == [[2, 3], [6, 7], [9]]
+    # a tail batch smaller than the world: every rank still yields the same number of steps (empty shard)
+    got = [[t[0].tolist() for t in _batches((x[:9],), 4, order[:9], r, 2)] for r in range(2)]
+    assert got[0] == [[0, 1], [4, 5], [8]] and got[1] == [[2, 3], [6, 7], []]
+
+
+def _ragged_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from admmnet_b200.training import _batches, train_step
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Linear(4, 1, bias=False)
+
+    class M(torch.nn.Module):                      # stand-in with the (y, b, sigma) call signature of the net
+        def __init__(self):
+            super().__init__()
+            self.lin = net
+
+        def forward(self, y, b, sigma):
+            return self.lin(y)
+
+    model = M()
+    crit = lambda out, tgt: (((out - tgt) ** 2).sum() / out.shape[0], {})
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)          # lr 0: only the averaged .grad matters
+    X = torch.arange(20, dtype=torch.float32).view(5, 4) / 10
+    T = torch.ones(5, 1)
+    grads = []
+    for (xb, tb) in _batches((X, T), 4, torch.arange(5), rank, world):     # batches of 4 and 1: rank 1's tail is empty
+        train_step(model, crit, opt, xb, None, None, tb, max_norm=1e9)
+        grads.append(net.weight.grad.numpy().copy())
+    q.put((rank, grads))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_and_empty_shards_give_the_global_batch_gradient_gloo():
+    """a tail batch smaller than the world must neither hang nor mis-weight the average."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ragged_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Linear(4, 1, bias=False)
+    X = torch.arange(20, dtype=torch.float32).view(5, 4) / 10
+    want = []
+    for lo, hi in ((0, 4), (4, 5)):                 # per-sample mean over the GLOBAL batch
+        net.zero_grad()
+        (((net(X[lo:hi]) - 1.0) ** 2).sum() / (hi - lo)).backward()
+        want.append(net.weight.grad.numpy().copy())
+    for r in range(2):
+        assert len(res[r]) == 2
+        for g, w in zip(res[r], want):
+            assert np.allclose(g, w, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.gpu
