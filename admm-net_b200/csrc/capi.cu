@@ -16,6 +16,7 @@
 #include "gen_kernels.cu"
 #include "head_kernels.cu"
 #include "tc_probe.cu"
+#include "tail_tc.cu"
 
 using namespace admmnet;
 
@@ -101,6 +102,8 @@ extern "C" const char* admmnet_last_error(void) { return g_err.c_str(); }
 extern "C" int admmnet_version(void) { return 100; }
 extern "C" int admmnet_param_stride(int n) { return param_stride(n); }
 
+static long long* tc_prof_buffer();
+
 // ------------------------------------------------------------------------------------ workspace
 namespace {
 struct Ws {
@@ -164,8 +167,9 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     w.Zp = (float2*)take(B * npk * sizeof(float2));
     w.GV = (float2*)take(B * npk * sizeof(float2));
     // two scratch slots so that consecutive chunks can be in flight on different streams
-    w.Zr = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
-    w.Zr2 = (float*)take((size_t)NSLOT * C * d * d * sizeof(float));
+    const size_t zsz = (size_t)d * (4 * ((d + 3) / 4));          // Z^T per signal: d rows of pitch 4*ceil(d/4)
+    w.Zr = (float*)take((size_t)NSLOT * C * zsz * sizeof(float));
+    w.Zr2 = (float*)take((size_t)NSLOT * C * zsz * sizeof(float));
     w.rho = (double*)take((size_t)NSLOT * C * DC_MAXTEAR * sizeof(double));
     w.rot = (float2*)take((size_t)NSLOT * C * rcap * sizeof(float2));
     w.tau = (float2*)take((size_t)NSLOT * C * d * sizeof(float2));
@@ -317,6 +321,25 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         t.Pk = Pk; t.r_out = w.r; t.U_out = U_out; t.lamp_out = lamp_out;
         t.B = B; t.n = n; t.d = d; t.ldu = 4 * ((d + 3) / 4); t.with_c = with_c; t.skip = skip;
         prof::Scope pscope(prof::TAIL, st);
+        // tensor-core form (tcgen05/TMEM, Z^T by TMA): production sizes, no eigenvector tap, positive eigenvalue map
+        static const bool use_tc = !(getenv("ADMMNET_TAILTC") && atoi(getenv("ADMMNET_TAILTC")) == 0);
+        TailTcPlan plan;
+        if (use_tc && with_c >= 0 && Pk && !U_out && !lamp_out && !skip && tail_tc_plan(d, plan)) {
+            TailTcArgs ta;
+            ta.Zr = zfinal; ta.GV = w.GV; ta.tau = w.tau; ta.lam = w.lam; ta.phi_cur = w.phi_cur; ta.h_cur = w.h_cur;
+            ta.Pk = Pk; ta.r_out = w.r; ta.B = B; ta.n = n; ta.with_c = with_c; ta.plan = plan;
+            ta.prof = tc_prof_buffer();
+            CUtensorMap tmZ;
+            if (!make_tmap_2d_f32(&tmZ, zfinal, (uint64_t)B * d, plan.ldz, (uint64_t)plan.ldz * 4, d, plan.ldz))
+                return fail(ADMMNET_ERR_CUDA, "cuTensorMapEncodeTiled failed for the Z^T scratch");
+            int dev = 0, nsm = 0;
+            CK(cudaGetDevice(&dev));
+            CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+            CK(cudaFuncSetAttribute(k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
+            k_tail_tc<<<B < nsm ? B : nsm, TC_NT, plan.total, st>>>(ta, tmZ);
+            CK(cudaGetLastError());
+            return 0;
+        }
         static const bool persistent = !(getenv("ADMMNET_TAILP") && atoi(getenv("ADMMNET_TAILP")) == 0);
         const size_t smp = tailp_smem_bytes(d, t.ldu);
         if (persistent && d <= 104 && with_c > 0 && !U_out && !lamp_out && !skip && smp <= 227 * 1024) {
@@ -348,8 +371,8 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
 static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0, int rcap = 0) {
     Ws c = w;
     const size_t npk = (size_t)d * (d + 1) / 2;
-    c.Zr += (size_t)slot * C * d * d;
-    c.Zr2 += (size_t)slot * C * d * d;
+    c.Zr += (size_t)slot * C * d * (4 * ((d + 3) / 4));
+    c.Zr2 += (size_t)slot * C * d * (4 * ((d + 3) / 4));
     c.rho += (size_t)slot * C * DC_MAXTEAR;
     c.rot += (size_t)slot * C * rcap;
     c.tau += (size_t)slot * C * d;
@@ -688,8 +711,10 @@ extern "C" int admm_classic_forward(const void* y, const void* b, int in_is_c128
     cudaStream_t st = (cudaStream_t)stream;
     prof::Scope pscope(prof::CLASSIC, st);
     static const int gl_env = getenv("ADMMNET_CLASSIC_GL") ? atoi(getenv("ADMMNET_CLASSIC_GL")) : 0;
+    // measured on B200 at batch 65536, n = 100 (tools/classic_ab.py): 5 iterations 32 lanes 95 us / 16 lanes 115 us /
+    // 8 lanes 167 us; 100 iterations 665 / 503 / 536 us -> 32 lanes per signal for short runs, 16 for long ones
     const int gl = (gl_env == 8 && n <= 104) ? 8 : (gl_env == 16 && n <= 112) ? 16 : (gl_env == 32) ? 32
-                   : (n <= 104 ? 8 : 32);
+                   : ((n_iter > 20 && n <= 112) ? 16 : 32);
     const int grid = (int)(((long long)B * gl + 255) / 256);      // one group of gl lanes per signal
 #define CLASSIC_LAUNCH(T, E, G) k_classic<T, E, G><<<grid, 256, 0, st>>>((const T*)y, (const T*)b, B, n, rho, n_iter, (double2*)phi_out)
     if (gl == 8) {
@@ -755,7 +780,8 @@ extern "C" int admmnet_tc_gemm_probe(const float* A, const float* B, const float
                                      float* out, void* stream) {
     if (!A || !B || !out) return fail(ADMMNET_ERR_ARG, "null pointer");
     if (N < 8 || N > 256 || (N % 8) || K < 8 || K > 64 || (K % 8)) return fail(ADMMNET_ERR_ARG, "need N in [8,256] step 8, K in [8,64] step 8");
-    if ((flags & TCP_A_TMEM) && (flags & TCP_A_MN)) return fail(ADMMNET_ERR_ARG, "A in TMEM has no major-ness");
+    if (flags & (TCP_A_MN | TCP_B_MN))
+        return fail(ADMMNET_ERR_ARG, "MN-major staging is not supported (the tail kernel only uses K-major tiles)");
     const size_t sm = 1024 + (size_t)(3 * 128 + 3 * N) * K * sizeof(float);
     if (sm > 227 * 1024) return fail(ADMMNET_ERR_ARG, "probe tile does not fit shared memory");
     TcProbeArgs a;
@@ -771,6 +797,36 @@ extern "C" int admmnet_tc_gemm_probe(const float* A, const float* B, const float
     k_tc_probe<<<1, 128, sm, (cudaStream_t)stream>>>(a, tmA, tmB);
     CK(cudaGetLastError());
     return 0;
+}
+
+// Per-phase clock counters of k_tail_tc (CTA 0, summed over launches) when ADMMNET_TC_PROF=1: a tuning aid.
+static long long* tc_prof_buffer() {
+    static long long* buf = [] {
+        long long* p = nullptr;
+        if (getenv("ADMMNET_TC_PROF") && atoi(getenv("ADMMNET_TC_PROF")) != 0) {
+            if (cudaMalloc(&p, 16 * sizeof(long long)) != cudaSuccess) p = nullptr;
+            else cudaMemset(p, 0, 16 * sizeof(long long));
+        }
+        return p;
+    }();
+    return buf;
+}
+extern "C" int admmnet_tail_tc_profile_read(long long* host16) {
+    if (!host16) return fail(ADMMNET_ERR_ARG, "null pointer");
+    long long* p = tc_prof_buffer();
+    if (!p) { memset(host16, 0, 16 * sizeof(long long)); return 0; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host16, p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p, 0, 16 * sizeof(long long)));
+    return 0;
+}
+
+// shared-memory bytes of the tensor-core tail kernel for matrix order d, or -1 when d is outside its range (then the
+// SIMT tail kernels serve); 0 when it is switched off (ADMMNET_TAILTC=0)
+extern "C" int admmnet_tail_tc_smem_bytes(int d) {
+    if (getenv("ADMMNET_TAILTC") && atoi(getenv("ADMMNET_TAILTC")) == 0) return 0;
+    TailTcPlan plan;
+    return tail_tc_plan(d, plan) ? plan.total : -1;
 }
 
 // ------------------------------------------------------------------------------------ FP32 FMA peak

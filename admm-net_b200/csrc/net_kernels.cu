@@ -844,8 +844,10 @@ k_rot(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, in
         __syncwarp();   // stage buffer (ch&1) is refilled by issue(ch+2)
     }
     __syncwarp();
-    float* outz = Zt + (size_t)sig * d * d;
-    for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldr + (idx % d)];
+    // global Z^T keeps the padded row pitch ldr (16-byte aligned rows: TMA box source for k_tail_tc)
+    float4* outz = reinterpret_cast<float4*>(Zt + (size_t)sig * d * ldr);
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    for (int idx = lane; idx < d * ldr / 4; idx += 32) outz[idx] = z4[idx];
 }
 
 // k_rotf: k_rot with PAIRS of consecutive sweeps fused.  k_rot is bound by shared-memory bandwidth (one 128-bit load
@@ -1049,8 +1051,10 @@ k_rotf(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, i
     }
 #undef RING
     __syncwarp();
-    float* outz = Zt + (size_t)sig * d * d;
-    for (int idx = lane; idx < d * d; idx += 32) outz[idx] = z[(idx / d) * ldr + (idx % d)];
+    // global Z^T keeps the padded row pitch ldr (16-byte aligned rows: TMA box source for k_tail_tc)
+    float4* outz = reinterpret_cast<float4*>(Zt + (size_t)sig * d * ldr);
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    for (int idx = lane; idx < d * ldr / 4; idx += 32) outz[idx] = z4[idx];
 }
 
 // =====================================================================================
@@ -1175,11 +1179,11 @@ __global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
     const int tid = threadIdx.x;
     const int sig = blockIdx.x;
     if (a.skip && a.skip[sig]) return;
-    const float* Zg = a.Zin + (size_t)sig * d * d;
-    float* Zo = a.Zout + (size_t)sig * d * d;
+    const float* Zg = a.Zin + (size_t)sig * d * ldr;        // global pitch = ldr (see k_rot)
+    float* Zo = a.Zout + (size_t)sig * d * ldr;
     float* lam = a.lam + (size_t)sig * d;
 
-    for (int idx = tid; idx < d * d; idx += MG_THREADS) Zs[(idx / d) * ldr + (idx % d)] = Zg[idx];
+    for (int idx = tid; idx < d * ldr; idx += MG_THREADS) Zs[idx] = Zg[idx];
     for (int idx = tid; idx < d * ldr; idx += MG_THREADS) Ws[idx] = 0.f;
     if (tid == 0) *nrotl = 0;
     __syncthreads();
@@ -1376,7 +1380,7 @@ __global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
     __syncthreads();
     // ---- every column is copied first (deflated pairs keep theirs; rows outside a block are zero), then the
     //      non-deflated ones are overwritten by Q * W (4 rows x 4 roots per thread)
-    for (int idx = tid; idx < d * d; idx += MG_THREADS) Zo[idx] = Zs[(idx / d) * ldr + (idx % d)];
+    for (int idx = tid; idx < d * ldr; idx += MG_THREADS) Zo[idx] = Zs[idx];
     __syncthreads();
     for (int r = 0; r < a.nr; ++r) {
         const int ra = a.ra[r], rb = a.rb[r], k = kcnt[r];
@@ -1407,7 +1411,7 @@ __global__ void __launch_bounds__(MG_THREADS, 2) k_merge(MergeArgs a) {
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 if (t0 + y >= k) continue;
-                float* oc = Zo + (size_t)kcol[ra + t0 + y] * d;
+                float* oc = Zo + (size_t)kcol[ra + t0 + y] * ldr;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     const int rr = r0 + x;
@@ -1523,7 +1527,7 @@ __device__ __forceinline__ float rebuild_lower(const float2* __restrict__ U, int
 // rows s+8j kept in registers for all d-1 reflectors -> no block barrier inside that phase.
 // =====================================================================================
 struct TailArgs {
-    const float* Zr;        // [B][d][d]  Z transposed: Zr[c][r]
+    const float* Zr;        // [B][d][ldz]  Z transposed: Zr[c][r], row pitch ldz = 4*ceil(d/4)
     float2* GV;             // [B][npk]: reflectors on entry, G packed lower on exit
     const float2* tau;      // [B][d]
     const float* lam;       // [B][d]
@@ -1563,8 +1567,9 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
     // ---- phase A: stage reflectors, Z, per-signal vectors
     for (int idx = tid; idx < nv; idx += NT) Vs[idx] = GV[idx];
     float* Zs = reinterpret_cast<float*>(U);
-    const float* Zg = a.Zr + (size_t)sig * d * d;
-    for (int idx = tid; idx < d * d; idx += NT) Zs[idx] = Zg[idx];
+    const int ldz = 4 * ((d + 3) / 4);                        // row pitch of the global Z^T (k_rot)
+    const float* Zg = a.Zr + (size_t)sig * d * ldz;
+    for (int idx = tid; idx < d * ldz; idx += NT) Zs[idx] = Zg[idx];
     for (int i = tid; i < d; i += NT) {
         taus[i] = a.tau[(size_t)sig * d + i];
         const float l = a.lam[(size_t)sig * d + i];
@@ -1590,7 +1595,7 @@ __global__ void __launch_bounds__(NT, 1) k_tail(TailArgs a) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
         const int r = s8 + RL * j;
-        Mx[j] = pk2((r < d && c0 < d) ? Zs[c0 * d + r] : 0.f, (r < d && c1 < d) ? Zs[c1 * d + r] : 0.f);
+        Mx[j] = pk2((r < d && c0 < d) ? Zs[c0 * ldz + r] : 0.f, (r < d && c1 < d) ? Zs[c1 * ldz + r] : 0.f);
         My[j] = pk2(0.f, 0.f);
     }
     __syncthreads();   // Z staging area is dead from here on (becomes U)
@@ -1685,7 +1690,7 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 // =====================================================================================
 __host__ __device__ inline size_t tailp_smem_bytes(int d, int ldu) {
     const size_t nv2 = ((size_t)d * (d - 1) / 2 + 1) & ~(size_t)1;
-    const size_t zf = ((size_t)d * d + 3) & ~(size_t)3;
+    const size_t zf = (size_t)d * (4 * ((d + 3) / 4));
     return ((size_t)d * ldu + 2 * nv2 + 2 * 128 /*tau*/ + 2 * 128 /*phi*/) * sizeof(float2) +
            (zf + 2 * 128 /*lam*/ + 2 * 128 /*h*/ + 128 /*lamp*/ + 96) * sizeof(float);
 }
@@ -1695,7 +1700,8 @@ __global__ void __launch_bounds__(NT, 1) k_tail_p(TailArgs a) {
     const int n = a.n, d = a.d, ldu = a.ldu;
     const int nv = d * (d - 1) / 2;
     const int nv2 = (nv + 1) & ~1;
-    const int zf = (d * d + 3) & ~3;
+    const int ldz = 4 * ((d + 3) / 4);                        // row pitch of the global Z^T (k_rot)
+    const int zf = d * ldz;
     float2* U = reinterpret_cast<float2*>(smem_raw);          // [d][ldu] column-major
     float2* Vb = U + (size_t)d * ldu;                         // [2][nv2] reflectors
     float2* taub = Vb + 2 * (size_t)nv2;                      // [2][128]
@@ -1714,8 +1720,8 @@ __global__ void __launch_bounds__(NT, 1) k_tail_p(TailArgs a) {
         const float2* gv = a.GV + (size_t)sig * npk;
         float2* vd = Vb + (size_t)buf * nv2;
         for (int idx = tid; idx < nv; idx += NT) cp_async8(vd + idx, gv + idx);
-        const float* zg = a.Zr + (size_t)sig * d * d;
-        for (int idx = tid; idx < d * d; idx += NT) cp_async4(Zn + idx, zg + idx);
+        const float* zg = a.Zr + (size_t)sig * zf;
+        for (int idx = tid; idx < zf / 4; idx += NT) cp_async16(Zn + 4 * idx, zg + 4 * idx);
         for (int i = tid; i < d; i += NT) {
             cp_async8(taub + buf * 128 + i, a.tau + (size_t)sig * d + i);
             cp_async4(lamb + buf * 128 + i, a.lam + (size_t)sig * d + i);
@@ -1744,7 +1750,7 @@ __global__ void __launch_bounds__(NT, 1) k_tail_p(TailArgs a) {
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             const int r = s8 + RL * j;
-            Mx[j] = pk2((r < d && c0 < d) ? Zn[c0 * d + r] : 0.f, (r < d && c1 < d) ? Zn[c1 * d + r] : 0.f);
+            Mx[j] = pk2((r < d && c0 < d) ? Zn[c0 * ldz + r] : 0.f, (r < d && c1 < d) ? Zn[c1 * ldz + r] : 0.f);
             My[j] = pk2(0.f, 0.f);
         }
         if (tid < d) lamp[tid] = eig_map(P, lamb[buf * 128 + tid]);

@@ -1,0 +1,585 @@
+// k_tail_tc: the tensor-core form of k_tail_p (layers >= 1 of admmnet_forward, n = 100 class sizes, d <= 104).
+//
+//   U = Q_H Z  (back-transformation of the real eigenvectors of T, reference: second half of torch.linalg.eigh,
+//               admm_net.py:303),   l' = f(l) (admm_net.py:310-334),
+//   G = U diag(l') U^H (admm_net.py:343-352),   r = ||G - C||_F (admm_net.py:454)
+//
+// Both contractions run on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators and the running
+// eigenvector matrix in tensor memory), at fp32 accuracy through the 3xTF32 split a*b ~ ah*bh + ah*bl + al*bh
+// (ah = rna_tf32(a), al = a - ah).  Z^T arrives by TMA (cp.async.bulk.tensor.2d), one box per signal.
+//
+// Data layout.  X = U^T lives in TMEM: lane i = eigenvector i, columns = coordinates; the real plane occupies columns
+// a (0..dp-1), the imaginary plane is stored column-REVERSED at 2dp-1-a, so the coordinates a >= a0 touched by a block
+// of reflectors form ONE contiguous window [a0, 2dp-a0).  X is kept as an exact pair (hi, lo): hi = rna_tf32(x) in
+// columns [0, 2dp), lo = x - hi in [2dp, 4dp); updates are accumulated into lo by the MMA (fp32 accumulator), then a
+// re-split pass restores the invariant.  P (the block's projections) sits in [4dp, 4dp+96).
+//
+// Back-transformation, reflectors k = 0..d-2 (H_k = I - tau_k v_k v_k^H, U <- H_0 H_1 ... H_{d-2} Z):
+//   * the trailing `rem` <= 8 reflectors only touch the last rem coordinates: applied per thread on its own row;
+//   * the others in blocks of NB = 24 from the last block to the first, compact WY:  Q_j = I - V_j T_j V_j^H,
+//         X <- X - P Y^T,   P = X conj(V_j)   (GEMM 1: M=128, N=48 [Pr|Pi], K = window),
+//                           Y = V_j T_j       (GEMM 2: M=128, N = window, K = 24, for A = Pr and A = Pi).
+//     Y is obtained without forming T: row a of Y solves  y (diag(1/tau) + striu(S)) = v_a,  S = V_j^H V_j, one
+//     thread per (block, coordinate) - 256 independent substitutions for d = 101.
+// Rebuild: W = sqrt(l')_i X (l' > 0 always, admm_net.py:321-331), staged K-major [coordinate][eigen index] in shared
+// memory; G_r = Wr Wr^T + Wi Wi^T, G_i = Wi Wr^T - Wr Wi^T : 4 products x 3 split terms x dp/8 K-steps of M=128,
+// N=dp MMAs into TMEM columns [0, 2dp).  Epilogue: lower triangle -> residual norm, packed store through shared
+// memory (coalesced).
+//
+// Persistent: one CTA per SM (219 KB of shared memory, all 512 TMEM columns); the next signal's reflectors and small
+// vectors stream in with cp.async while the current one is rebuilt, its Z^T by TMA during the epilogue.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace admmnet {
+
+constexpr int TC_NB = 24;            // reflectors per block (P occupies 4*NB = 96 TMEM columns)
+constexpr int TC_NT = 256;           // 8 warps: warp w works on TMEM lanes 32*(w&3).., column groups of parity w>>2
+constexpr int TC_MAXBLK = 5;
+constexpr int TC_LOCAL_MAX = 8;
+
+struct TailTcPlan {
+    int d, dp, ldz;                  // matrix order, d rounded up to 8, row pitch of Z^T
+    int nblk, nloc;                  // WY blocks, trailing reflectors applied per thread
+    int k0[TC_MAXBLK], nb[TC_MAXBLK], a0[TC_MAXBLK], yoff[TC_MAXBLK];   // first reflector, count, window start, row offset in Yall
+    int yrows;                       // sum over blocks of (d - 1 - k0)
+    // shared-memory byte offsets
+    int off_tiles, off_yall, off_z, off_vs, off_small, total;
+    int lbo_w;                       // K-chunk stride of a W tile (odd multiple of 16 bytes)
+};
+
+inline __host__ bool tail_tc_plan(int d, TailTcPlan& p) {
+    if (d < 33 || d > 104) return false;
+    p.d = d; p.dp = (d + 7) & ~7; p.ldz = 4 * ((d + 3) / 4);
+    const int nref = d - 1;
+    int nfull = nref / TC_NB, rem = nref - nfull * TC_NB;
+    p.nblk = nfull; p.nloc = rem;
+    if (rem > TC_LOCAL_MAX) { p.nblk = nfull + 1; p.nloc = 0; }
+    if (p.nblk < 1 || p.nblk > TC_MAXBLK) return false;
+    p.yrows = 0;
+    for (int j = 0; j < p.nblk; ++j) {
+        p.k0[j] = j * TC_NB;
+        p.nb[j] = (j < nfull) ? TC_NB : rem;
+        p.a0[j] = (p.k0[j] + 1) & ~7;
+        p.yoff[j] = p.yrows;
+        p.yrows += d - 1 - p.k0[j];
+    }
+    auto al = [](int x) { return (x + 127) & ~127; };
+    const int na_max = p.dp - p.a0[0];
+    const int tiles = 2 * (48 * 2 * na_max * 4);                // V tiles (hi, lo); the Y tiles have the same size
+    p.lbo_w = 16 * (p.dp | 1);
+    const int wbytes = 4 * (p.dp / 4) * p.lbo_w;                // 4 W tiles
+    p.off_tiles = 1024;
+    p.off_yall = p.off_tiles + al(tiles);
+    p.off_z = al(p.off_yall + p.yrows * TC_NB * 8);
+    int r0_end = p.off_z + al(d * p.ldz * 4);
+    if (r0_end < p.off_tiles + al(wbytes)) r0_end = p.off_tiles + al(wbytes);
+    const int gstage = d * (d + 1) / 2 * 8;
+    if (p.off_tiles + gstage > p.off_z) return false;           // G staging must not overlap the Z box
+    if (TC_MAXBLK * TC_NB * TC_NB * 8 > al(tiles)) return false; // Gram matrices alias the tile area
+    p.off_vs = r0_end;
+    p.off_small = al(p.off_vs + d * (d - 1) / 2 * 8);
+    p.total = p.off_small + 2 * 128 * 8 /*tau*/ + 2 * 128 * 4 /*lam*/ + 2 * 128 * 8 /*phi*/ + 2 * 128 * 4 /*h*/ + 512;
+    return p.total <= 227 * 1024;
+}
+
+struct TailTcArgs {
+    const float* Zr;        // [B][d][ldz]
+    float2* GV;             // [B][npk]: reflectors on entry, G packed lower on exit
+    const float2* tau;      // [B][d]
+    const float* lam;       // [B][d]
+    const float2* phi_cur;  // [B][n]
+    const float* h_cur;     // [B][n]
+    const float* Pk;
+    float* r_out;           // [B]
+    int B, n, with_c;       // with_c = 0: plain f(A) (debug tap), no residual
+    long long* prof;        // optional [16]: clock cycles per phase, summed over the signals of CTA 0 (tuning aid)
+    TailTcPlan plan;
+};
+enum TcPhase { TCP_WAIT = 0, TCP_S1, TCP_GRAM, TCP_YSOLVE, TCP_VTILE, TCP_GEMM1, TCP_PSPLIT_YTILE, TCP_GEMM2, TCP_RESPLIT,
+               TCP_WSTAGE, TCP_REBUILD, TCP_EPILOGUE, TCP_SIGNALS, TCP_NPHASE };
+
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid_constant__ CUtensorMap tmZ) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TailTcPlan& pl = a.plan;
+    const int d = pl.d, dp = pl.dp, ldz = pl.ldz, n = a.n;
+    const int DP2 = 2 * dp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = 32 * q + lane;                       // TMEM lane = eigenvector index (phases on X), row of G (epilogue)
+    const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar_z = bar_mma + 1;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 16);
+    float* red = reinterpret_cast<float*>(smem + 64);    // [32]
+    float* tiles = reinterpret_cast<float*>(smem + pl.off_tiles);
+    float2* Sg = reinterpret_cast<float2*>(smem + pl.off_tiles);       // Gram matrices [blk][NB][NB] (alias, early)
+    float2* Yall = reinterpret_cast<float2*>(smem + pl.off_yall);      // [yrows][NB]
+    float* Zt = reinterpret_cast<float*>(smem + pl.off_z);             // [d][ldz] TMA box
+    float2* Vs = reinterpret_cast<float2*>(smem + pl.off_vs);          // packed reflectors
+    float2* taub = reinterpret_cast<float2*>(smem + pl.off_small);     // [2][128]
+    float2* phib = taub + 2 * 128;                                     // [2][128]
+    float* lamb = reinterpret_cast<float*>(phib + 2 * 128);            // [2][128]
+    float* hb = lamb + 2 * 128;                                        // [2][128]
+    float2* Gs = reinterpret_cast<float2*>(smem + pl.off_tiles);       // packed G staging (alias, late)
+
+    const int npk = d * (d + 1) / 2, nv = d * (d - 1) / 2;
+    const float* __restrict__ P = a.Pk;
+    const float c1z = (a.with_c > 0) ? P[P_C1Z] : 0.f;
+
+    if (tid == 0) {
+        tc::mbar_init(bar_mma, 1);
+        tc::mbar_init(bar_z, 1);
+        tc::mbar_fence_init();
+        tc::tma_prefetch_desc(&tmZ);
+    }
+    if (warp == 0) tc::tmem_alloc(tslot, 512);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tbase = *tslot;
+    const uint32_t tXhi = tbase, tXlo = tbase + DP2, tP = tbase + 2 * DP2;
+    uint32_t ph_mma = 0, ph_z = 0;
+
+    auto prefetch_small = [&](int sig, int buf) {
+        for (int i = tid; i < d; i += TC_NT) {
+            cp_async8(taub + buf * 128 + i, a.tau + (size_t)sig * d + i);
+            cp_async4(lamb + buf * 128 + i, a.lam + (size_t)sig * d + i);
+        }
+        if (a.with_c > 0)
+            for (int j = tid; j < n; j += TC_NT) {
+                cp_async8(phib + buf * 128 + j, a.phi_cur + (size_t)sig * n + j);
+                cp_async4(hb + buf * 128 + j, a.h_cur + (size_t)sig * n + j);
+            }
+    };
+    auto prefetch_vs = [&](int sig) {
+        const float2* gv = a.GV + (size_t)sig * npk;
+        for (int idx = tid; idx < nv; idx += TC_NT) cp_async8(Vs + idx, gv + idx);
+    };
+    auto load_z = [&](int sig) {                          // one thread: TMA box [d][ldz] of signal sig
+        tc::fence_async_smem();
+        tc::mbar_expect_tx(bar_z, (uint32_t)(d * ldz * sizeof(float)));
+        tc::tma_load_2d(Zt, &tmZ, 0, sig * d, bar_z);
+    };
+    // wait for all MMAs committed so far; every thread observes every phase
+    auto wait_mma = [&]() {
+        tc::mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc::tc_fence_after_sync();
+    };
+    // TMEM / shared-memory writes of all threads -> visible to the MMAs the issuing thread is about to launch
+    auto publish = [&]() {
+        tc::tmem_wait_st();
+        tc::tmem_wait_ld();
+        tc::fence_async_smem();
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        tc::tc_fence_after_sync();
+    };
+
+    long long pacc[TCP_NPHASE];
+#pragma unroll
+    for (int i = 0; i < TCP_NPHASE; ++i) pacc[i] = 0;
+    const bool profiling = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tlast = profiling ? clock64() : 0;
+#define TC_MARK(PH)                                 \
+    if (profiling) {                                \
+        const long long tnow = clock64();           \
+        pacc[PH] += tnow - tlast;                   \
+        tlast = tnow;                               \
+    }
+
+    int buf = 0;
+    if ((int)blockIdx.x < a.B) {
+        prefetch_small(blockIdx.x, 0);
+        prefetch_vs(blockIdx.x);
+        cp_async_commit();
+        if (tid == 0) load_z(blockIdx.x);
+    }
+    for (int sig = blockIdx.x; sig < a.B; sig += gridDim.x, buf ^= 1) {
+        const float2* taus = taub + buf * 128;
+        const float2* phis = phib + buf * 128;
+        const float* hs = hb + buf * 128;
+        const bool has_next = sig + (int)gridDim.x < a.B;
+        cp_async_wait<0>();
+        tc::mbar_wait(bar_z, ph_z);
+        ph_z ^= 1;
+        __syncthreads();
+        TC_MARK(TCP_WAIT)
+
+        // ================= S1: X <- Z^T (trailing reflectors applied per row), split into TMEM =================
+        float sl = 0.f;                                                   // sqrt(l'_row)
+        if (row < d) {
+            const float l = lamb[buf * 128 + row];
+            sl = sqrtf(eig_map(P, l));
+        }
+        {
+            const int aL = d - pl.nloc;                                   // first coordinate touched locally
+            float ur[TC_LOCAL_MAX], ui[TC_LOCAL_MAX];
+#pragma unroll
+            for (int e = 0; e < TC_LOCAL_MAX; ++e) {
+                ur[e] = (row < d && e < pl.nloc) ? Zt[row * ldz + aL + e] : 0.f;
+                ui[e] = 0.f;
+            }
+            // reflectors k = d-2 down to d-1-nloc; v_k lives on coordinates k+1.. = local index e >= k+1-aL
+            for (int k = d - 2; k >= d - 1 - pl.nloc; --k) {
+                const float2 tk = taus[k];
+                const int vb = voff(k, d) - (k + 1);
+                float dx = 0.f, dy = 0.f;                                 // v^H u
+#pragma unroll
+                for (int e = 0; e < TC_LOCAL_MAX; ++e) {
+                    const int r = aL + e;
+                    if (r > k && r < d) {
+                        const float2 v = Vs[vb + r];
+                        dx += v.x * ur[e] + v.y * ui[e];
+                        dy += v.x * ui[e] - v.y * ur[e];
+                    }
+                }
+                const float2 t = cmul(tk, make_float2(dx, dy));
+#pragma unroll
+                for (int e = 0; e < TC_LOCAL_MAX; ++e) {
+                    const int r = aL + e;
+                    if (r > k && r < d) {
+                        const float2 v = Vs[vb + r];
+                        ur[e] -= v.x * t.x - v.y * t.y;
+                        ui[e] -= v.x * t.y + v.y * t.x;
+                    }
+                }
+            }
+            // column groups of 8: real plane g -> columns 8g.., imaginary plane -> reversed columns
+            const int ngr = dp / 8;
+            for (int g = hh; g < 2 * ngr; g += 2) {
+                uint32_t vh[8], vl[8];
+                const bool im = g >= ngr;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int acol = im ? (DP2 - 1 - (8 * g + jj)) : (8 * g + jj);      // coordinate of TMEM column 8g+jj
+                    float x = 0.f;
+                    if (row < d && acol < d) {
+                        if (acol >= aL) {
+                            // local-reflector coordinates: registers (static index through the unrolled select)
+                            float xr = 0.f, xi = 0.f;
+#pragma unroll
+                            for (int e = 0; e < TC_LOCAL_MAX; ++e)
+                                if (acol - aL == e) { xr = ur[e]; xi = ui[e]; }
+                            x = im ? xi : xr;
+                        } else if (!im) {
+                            x = Zt[row * ldz + acol];
+                        }
+                    }
+                    const float h = rna_tf32(x);
+                    vh[jj] = __float_as_uint(h);
+                    vl[jj] = __float_as_uint(x - h);
+                }
+                tc::tmem_st8(tXhi + lane_off + 8 * g, vh);
+                tc::tmem_st8(tXlo + lane_off + 8 * g, vl);
+            }
+        }
+
+        TC_MARK(TCP_S1)
+        // ================= S2: Gram matrices and Y = V T for all blocks (SIMT) =================
+        for (int p = tid; p < pl.nblk * TC_NB * TC_NB; p += TC_NT) {
+            const int j = p / (TC_NB * TC_NB), c1 = (p / TC_NB) % TC_NB, c2 = p % TC_NB;
+            float2 acc = make_float2(0.f, 0.f);
+            if (c1 < c2 && c2 < pl.nb[j]) {
+                const int ka = pl.k0[j] + c1, kb = pl.k0[j] + c2;
+                const float2* va = Vs + voff(ka, d) - (ka + 1);
+                const float2* vb2 = Vs + voff(kb, d) - (kb + 1);
+                float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
+                int r = kb + 1;
+                for (; r + 1 < d; r += 2) {
+                    const float2 x0 = va[r], y0 = vb2[r], x1 = va[r + 1], y1 = vb2[r + 1];
+                    ax = fmaf(x0.x, y0.x, ax); ax = fmaf(x0.y, y0.y, ax);
+                    ay = fmaf(x0.x, y0.y, ay); ay = fmaf(-x0.y, y0.x, ay);
+                    bx = fmaf(x1.x, y1.x, bx); bx = fmaf(x1.y, y1.y, bx);
+                    by = fmaf(x1.x, y1.y, by); by = fmaf(-x1.y, y1.x, by);
+                }
+                if (r < d) {
+                    const float2 x0 = va[r], y0 = vb2[r];
+                    ax = fmaf(x0.x, y0.x, ax); ax = fmaf(x0.y, y0.y, ax);
+                    ay = fmaf(x0.x, y0.y, ay); ay = fmaf(-x0.y, y0.x, ay);
+                }
+                acc = make_float2(ax + bx, ay + by);                       // conj(v_c1) . v_c2
+            }
+            Sg[p] = acc;
+        }
+        __syncthreads();
+        TC_MARK(TCP_GRAM)
+        for (int item = tid; item < pl.yrows; item += TC_NT) {
+            int j = 0;
+#pragma unroll
+            for (int jj = 1; jj < TC_MAXBLK; ++jj)
+                if (jj < pl.nblk && item >= pl.yoff[jj]) j = jj;
+            const int k0 = pl.k0[j];
+            const int arow = k0 + 1 + (item - pl.yoff[j]);                 // coordinate of this row of Y
+            const float2* S = Sg + j * TC_NB * TC_NB;
+            float2 y[TC_NB];
+#pragma unroll
+            for (int c = 0; c < TC_NB; ++c) {
+                const int k = k0 + c;
+                float2 v = make_float2(0.f, 0.f);
+                float2 tk = make_float2(0.f, 0.f);
+                if (c < pl.nb[j]) {
+                    tk = taus[k];
+                    if (arow > k) v = Vs[voff(k, d) - (k + 1) + arow];
+                }
+                float sx0 = v.x, sy0 = v.y, sx1 = 0.f, sy1 = 0.f;
+#pragma unroll
+                for (int m = 0; m < c; ++m) {
+                    const float2 s = S[m * TC_NB + c];
+                    if (m & 1) {
+                        sx1 = fmaf(-y[m].x, s.x, sx1); sx1 = fmaf(y[m].y, s.y, sx1);
+                        sy1 = fmaf(-y[m].x, s.y, sy1); sy1 = fmaf(-y[m].y, s.x, sy1);
+                    } else {
+                        sx0 = fmaf(-y[m].x, s.x, sx0); sx0 = fmaf(y[m].y, s.y, sx0);
+                        sy0 = fmaf(-y[m].x, s.y, sy0); sy0 = fmaf(-y[m].y, s.x, sy0);
+                    }
+                }
+                y[c] = cmul(tk, make_float2(sx0 + sx1, sy0 + sy1));
+            }
+            float4* dst = reinterpret_cast<float4*>(Yall + (size_t)item * TC_NB);
+#pragma unroll
+            for (int c = 0; c < TC_NB; c += 2) dst[c / 2] = make_float4(y[c].x, y[c].y, y[c + 1].x, y[c + 1].y);
+        }
+        __syncthreads();       // Yall complete; the Gram area (tile region) may be overwritten
+        TC_MARK(TCP_YSOLVE)
+
+        // ================= blocks, last to first =================
+        for (int j = pl.nblk - 1; j >= 0; --j) {
+            const int k0 = pl.k0[j], nbj = pl.nb[j], a0 = pl.a0[j];
+            const int Na = dp - a0, K2 = 2 * Na;
+            float* Vhi = tiles;
+            float* Vlo = tiles + 48 * K2;
+            // ---- V tiles: rows rho < 24: [Vr(a) | Vi(rev a)], rows 24..47: [-Vi(a) | Vr(rev a)], K-major, LBO = 48*16
+            for (int idx = tid; idx < TC_NB * Na; idx += TC_NT) {
+                const int c = idx % TC_NB, ar = idx / TC_NB, acol = a0 + ar, k = k0 + c;
+                float2 v = make_float2(0.f, 0.f);
+                if (c < nbj && acol > k && acol < d) v = Vs[voff(k, d) - (k + 1) + acol];
+                const int k1 = ar, k2 = K2 - 1 - ar;
+                const int o_r1 = (k1 >> 2) * 192 + c * 4 + (k1 & 3), o_r2 = (k2 >> 2) * 192 + c * 4 + (k2 & 3);
+                const int o_i1 = o_r1 + TC_NB * 4, o_i2 = o_r2 + TC_NB * 4;
+                const float hr = rna_tf32(v.x), hi_ = rna_tf32(v.y);
+                const float lr = v.x - hr, li = v.y - hi_;
+                Vhi[o_r1] = hr;  Vlo[o_r1] = lr;        // Pr row, real-plane position
+                Vhi[o_r2] = hi_; Vlo[o_r2] = li;        // Pr row, imaginary-plane position
+                Vhi[o_i1] = -hi_; Vlo[o_i1] = -li;      // Pi row, real-plane position
+                Vhi[o_i2] = hr;  Vlo[o_i2] = lr;        // Pi row, imaginary-plane position
+            }
+            if (j == 0 && has_next) {                    // last use of the reflectors and of tau: fetch the next signal's
+                __syncthreads();
+                prefetch_vs(sig + gridDim.x);
+                prefetch_small(sig + gridDim.x, buf ^ 1);
+            }
+            cp_async_commit();
+            publish();
+            TC_MARK(TCP_VTILE)
+            // ---- GEMM 1: [Pr | Pi] = X(window) * Vtile^T, 3 split terms
+            if (tid == 0) {
+                const uint32_t idesc = tc::idesc_tf32(128, 48);
+                const uint32_t vhi = tc::smem_u32(Vhi), vlo = tc::smem_u32(Vlo);
+                uint32_t acc = 0;
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t xa = (term == 2 ? tXlo : tXhi) + a0;
+                    const uint32_t vb = term == 1 ? vlo : vhi;
+                    for (int ks = 0; ks < K2 / 8; ++ks) {
+                        tc::mma_tf32_ts(tP, xa + 8 * ks, tc::smem_desc(vb + ks * 2 * 768, 768, 128), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                tc::mma_commit(bar_mma);
+            }
+            wait_mma();
+            TC_MARK(TCP_GEMM1)
+            // ---- P split (in place) and Y tiles
+            for (int g = hh; g < 6; g += 2) {
+                uint32_t v[8], vh[8], vl[8];
+                tc::tmem_ld8(tP + lane_off + 8 * g, v);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float x = __uint_as_float(v[jj]);
+                    const float h = rna_tf32(x);
+                    vh[jj] = __float_as_uint(h);
+                    vl[jj] = __float_as_uint(x - h);
+                }
+                tc::tmem_st8(tP + lane_off + 8 * g, vh);
+                tc::tmem_st8(tP + lane_off + 48 + 8 * g, vl);
+            }
+            // Y tiles (GEMM 1 has completed: the V tiles are dead).  Tile for A = Pr: rows [-Yr(a) | -Yi(rev a)],
+            // tile for A = Pi: rows [+Yi(a) | -Yr(rev a)]; K = c, LBO = K2*16.  Order: YPr_hi, YPr_lo, YPi_hi, YPi_lo.
+            float* YPr_hi = tiles;
+            float* YPr_lo = tiles + 6 * K2 * 4;
+            float* YPi_hi = tiles + 2 * 6 * K2 * 4;
+            float* YPi_lo = tiles + 3 * 6 * K2 * 4;
+            for (int idx = tid; idx < TC_NB * Na; idx += TC_NT) {
+                const int c = idx % TC_NB, ar = idx / TC_NB, acol = a0 + ar;
+                float2 yv = make_float2(0.f, 0.f);
+                if (acol > k0 && acol < d) yv = Yall[(size_t)(pl.yoff[j] + acol - (k0 + 1)) * TC_NB + c];
+                const int n1 = ar, n2 = K2 - 1 - ar;
+                const int o1 = (c >> 2) * (K2 * 4) + n1 * 4 + (c & 3), o2 = (c >> 2) * (K2 * 4) + n2 * 4 + (c & 3);
+                const float hr = rna_tf32(yv.x), hi_ = rna_tf32(yv.y);
+                const float lr = yv.x - hr, li = yv.y - hi_;
+                YPr_hi[o1] = -hr;  YPr_lo[o1] = -lr;
+                YPr_hi[o2] = -hi_; YPr_lo[o2] = -li;
+                YPi_hi[o1] = hi_;  YPi_lo[o1] = li;
+                YPi_hi[o2] = -hr;  YPi_lo[o2] = -lr;
+            }
+            publish();
+            TC_MARK(TCP_PSPLIT_YTILE)
+            // ---- GEMM 2: X_lo(window) += Pr * YPr^T + Pi * YPi^T, 3 split terms each
+            if (tid == 0) {
+                const uint32_t idesc = tc::idesc_tf32(128, K2);
+                const uint32_t lbo = (uint32_t)K2 * 16;
+                const uint32_t yb[4] = {tc::smem_u32(YPr_hi), tc::smem_u32(YPr_lo), tc::smem_u32(YPi_hi), tc::smem_u32(YPi_lo)};
+                for (int part = 0; part < 2; ++part) {        // A = Pr, Pi
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t pa = tP + (term == 2 ? 48 : 0) + part * TC_NB;
+                        const uint32_t tb = yb[2 * part + (term == 1 ? 1 : 0)];
+                        for (int ks = 0; ks < TC_NB / 8; ++ks)
+                            tc::mma_tf32_ts(tXlo + a0, pa + 8 * ks, tc::smem_desc(tb + ks * 2 * lbo, lbo, 128), idesc, 1);
+                    }
+                }
+                tc::mma_commit(bar_mma);
+            }
+            wait_mma();
+            TC_MARK(TCP_GEMM2)
+            // ---- re-split the window: x = hi + lo, hi' = rna(x), lo' = x - hi'   (last block: done by the W staging)
+            if (j > 0) {
+                for (int g = a0 / 8 + hh; g < (DP2 - a0) / 8; g += 2) {
+                    uint32_t vh[8], vl[8];
+                    tc::tmem_ld8(tXhi + lane_off + 8 * g, vh);
+                    tc::tmem_ld8(tXlo + lane_off + 8 * g, vl);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float x = __uint_as_float(vh[jj]) + __uint_as_float(vl[jj]);
+                        const float h = rna_tf32(x);
+                        vh[jj] = __float_as_uint(h);
+                        vl[jj] = __float_as_uint(x - h);
+                    }
+                    tc::tmem_st8(tXhi + lane_off + 8 * g, vh);
+                    tc::tmem_st8(tXlo + lane_off + 8 * g, vl);
+                }
+            }
+        }
+
+        TC_MARK(TCP_RESPLIT)
+        // ================= rebuild: W tiles, G = W W^H on the tensor cores =================
+        {
+            const int lbw = pl.lbo_w / 4;                                      // floats per K chunk
+            const int tsz = (dp / 4) * lbw;                                    // floats per W tile
+            float* Wt = tiles;                                                 // Wr_hi, Wr_lo, Wi_hi, Wi_lo
+            const int ngr = dp / 8;
+            const int kbase = (row >> 2) * lbw + (row & 3);
+            // (tcgen05.ld is warp-collective: every lane takes part, only the shared-memory stores are predicated)
+            for (int g = hh; g < 2 * ngr; g += 2) {
+                uint32_t vh[8], vl[8];
+                tc::tmem_ld8(tXhi + lane_off + 8 * g, vh);
+                tc::tmem_ld8(tXlo + lane_off + 8 * g, vl);
+                tc::tmem_wait_ld();
+                const bool im = g >= ngr;
+                float* Th = Wt + (im ? 2 * tsz : 0);
+                float* Tl = Th + tsz;
+                if (row < dp) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int acol = im ? (DP2 - 1 - (8 * g + jj)) : (8 * g + jj);
+                        const float w = sl * (__uint_as_float(vh[jj]) + __uint_as_float(vl[jj]));
+                        const float h = rna_tf32(w);
+                        Th[kbase + acol * 4] = h;
+                        Tl[kbase + acol * 4] = w - h;
+                    }
+                }
+            }
+            publish();
+            TC_MARK(TCP_WSTAGE)
+            if (tid == 0) {
+                const uint32_t w0 = tc::smem_u32(Wt);
+                const uint32_t tb[4] = {w0, w0 + (uint32_t)tsz * 4, w0 + 2u * tsz * 4, w0 + 3u * tsz * 4};   // rh rl ih il
+                const uint32_t lbo = (uint32_t)pl.lbo_w;
+                // G_r (columns [0,dp)) = Wr Wr^T + Wi Wi^T ; G_i (columns [dp,2dp)) = Wi Wr^T - Wr Wi^T
+                for (int prod = 0; prod < 4; ++prod) {
+                    const int ap = (prod == 0 || prod == 3) ? 0 : 1;           // A plane: r, i, i, r
+                    const int bp = (prod == 0 || prod == 2) ? 0 : 1;           // B plane: r, i, r, i
+                    const uint32_t dcol = tbase + (prod >= 2 ? dp : 0);
+                    const uint32_t idesc = tc::idesc_tf32(128, dp, prod == 3 ? 1 : 0);
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ta = tb[2 * ap + (term == 2 ? 1 : 0)], tbb = tb[2 * bp + (term == 1 ? 1 : 0)];
+                        for (int ks = 0; ks < dp / 8; ++ks) {
+                            const uint32_t acc = (prod == 0 || prod == 2) ? ((term | ks) ? 1u : 0u) : 1u;
+                            tc::mma_tf32_ss(dcol, tc::smem_desc(ta + ks * 2 * lbo, lbo, 128),
+                                            tc::smem_desc(tbb + ks * 2 * lbo, lbo, 128), idesc, acc);
+                        }
+                    }
+                }
+                tc::mma_commit(bar_mma);
+            }
+            wait_mma();
+        }
+        __syncthreads();                 // every thread is past the MMA wait: tile area and Z box are free
+        TC_MARK(TCP_REBUILD)
+        if (has_next && tid == 0) load_z(sig + gridDim.x);
+
+        // ================= epilogue: lower triangle of G -> residual, packed store =================
+        float rsq = 0.f;
+        {
+            const int ngr = dp / 8;
+            // warp-uniform trip count (the warp's last row is 32q+31); per-lane predicates only guard the stores
+            for (int g = hh; g < ngr && 8 * g <= 32 * q + 31; g += 2) {
+                uint32_t gr[8], gi[8];
+                tc::tmem_ld8(tbase + lane_off + 8 * g, gr);
+                tc::tmem_ld8(tbase + lane_off + dp + 8 * g, gi);
+                tc::tmem_wait_ld();
+                if (row < d) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int b = 8 * g + jj;
+                        if (b > row) continue;
+                        float2 gv = make_float2(__uint_as_float(gr[jj]), __uint_as_float(gi[jj]));
+                        if (b == row) gv.y = 0.f;
+                        Gs[pk(row, b)] = gv;
+                        if (a.with_c > 0) {
+                            float2 c = make_float2(0.f, 0.f);
+                            if (b == row) c.x = (row < n) ? hs[row] : c1z;
+                            else if (row == n) c = cconj(phis[b]);
+                            const float rx = gv.x - c.x, ry = gv.y - c.y;
+                            rsq += (b == row ? 1.f : 2.f) * (rx * rx + ry * ry);
+                        }
+                    }
+                }
+            }
+        }
+        tc::tmem_wait_ld();
+        tc::tc_fence_before_sync();
+        {
+            float v[1] = {rsq};
+            block_sum<1>(v, red);                        // two __syncthreads inside: Gs complete afterwards
+            if (tid == 0 && a.with_c > 0) a.r_out[sig] = sqrtf(v[0]);
+        }
+        tc::tc_fence_after_sync();
+        {
+            float2* GV = a.GV + (size_t)sig * npk;
+            for (int idx = tid; idx < npk; idx += TC_NT) GV[idx] = Gs[idx];
+        }
+        __syncthreads();                 // Gs (tile area) is reused by the next signal's Gram matrices
+        TC_MARK(TCP_EPILOGUE)
+        if (profiling) pacc[TCP_SIGNALS] += 1;
+    }
+    if (profiling) {
+#pragma unroll
+        for (int i = 0; i < TCP_NPHASE; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + i, (unsigned long long)pacc[i]);
+    }
+#undef TC_MARK
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+}  // namespace admmnet

@@ -13,6 +13,7 @@ enum TcProbeFlags : int {
     TCP_B_MN = 8,        // B staged MN-major
     TCP_TMA = 16,        // A and B brought in by TMA (cp.async.bulk.tensor.2d) into a row-major staging area first
     TCP_SPLIT3 = 32,     // 3xTF32: A, B are arbitrary fp32; hi/lo split on the fly, three MMAs per K step
+    TCP_DCOL8 = 64,      // accumulator at TMEM column 8 instead of 0 (windows of the tail kernel start at multiples of 8)
 };
 
 struct TcProbeArgs {
@@ -51,7 +52,7 @@ k_tc_probe(TcProbeArgs a, const __grid_constant__ CUtensorMap tmA, const __grid_
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tbase = *tslot;
-    const uint32_t tD = tbase;                 // columns [0, N): accumulator
+    const uint32_t tD = tbase + ((a.flags & TCP_DCOL8) ? 8 : 0);   // columns [0, N) or [8, N+8): accumulator
     const uint32_t tAhi = tbase + 256;         // columns [256, 256+K): A hi in TMEM
     const uint32_t tAlo = tbase + 256 + 64;    // A lo
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;

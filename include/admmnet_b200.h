@@ -172,9 +172,15 @@ int admmnet_fp32_peak_launch(float* out, int grid, int iters, double* flops, voi
 /* ---------------------------------------------------------------------------------------------
  * Debug tap of the tcgen05 / TMEM / TMA layer (csrc/tc.cuh) the tail kernel is built on: one 128 x N x K tf32 tile,
  * out = D0 + (+-A) * B^T, A [128][K], B [N][K], D0/out [128][N] row-major fp32 on the device.
- * flags: 1 A from tensor memory, 2 negate A, 4 A staged MN-major, 8 B staged MN-major, 16 operands loaded by TMA,
- * 32 3xTF32 split (arbitrary fp32 inputs, fp32-class result).  No reference counterpart (unit test of the machinery).
+ * flags: 1 A from tensor memory, 2 negate A, 16 operands loaded by TMA, 32 3xTF32 split (arbitrary fp32 inputs,
+ * fp32-class result), 64 accumulator at TMEM column 8.  No reference counterpart (unit test of the machinery).
  * ------------------------------------------------------------------------------------------- */
+/* shared-memory bytes of the tensor-core tail kernel (k_tail_tc) for matrix order d; -1: d outside its range
+ * (33..104, the SIMT tail kernels serve), 0: switched off with ADMMNET_TAILTC=0 */
+int admmnet_tail_tc_smem_bytes(int d);
+/* tuning aid: with ADMMNET_TC_PROF=1 in the environment k_tail_tc's CTA 0 accumulates clock cycles per phase
+ * (13 counters, csrc/tail_tc.cu enum TcPhase; the last one counts signals); reads and clears them. */
+int admmnet_tail_tc_profile_read(long long* host16);
 int admmnet_tc_gemm_probe(const float* A, const float* B, const float* D0, int N, int K, int flags, float* out,
                           void* stream);
 

@@ -183,6 +183,30 @@ def test_hermitian_function_matches_oracle(pkg):
     assert (G.to(torch.complex128) - Gt).abs().amax() / Gt.abs().amax() < 2e-5
 
 
+@pytest.mark.parametrize("d,B", [(101, 700), (104, 150), (97, 149), (72, 310), (65, 40), (40, 333), (33, 5)])
+def test_tensor_core_tail_kernel_sizes_and_persistence(pkg, d, B):
+    """k_tail_tc (tcgen05/TMEM back-transformation + rebuild, Z^T by TMA) through the f(A) tap: every block plan
+    (4 WY blocks + 4 thread-local reflectors at d = 101; padded last block at d = 65, 40; one block + 8 local at
+    d = 33), batches larger than the persistent grid (several signals per CTA, prefetch double buffering) and both
+    tridiagonal solvers in front of it (B > 1024 would be plain QL; here divide & conquer)."""
+    from admmnet_b200 import _capi
+    from admmnet_b200.params import pack_state_dict
+    from oracle import net_oracle
+    assert _capi.lib().admmnet_tail_tc_smem_bytes(d) > 0, "tensor-core tail kernel not selected"
+    z, sd = load_net_case("pert_k10")
+    P = pack_state_dict(sd, 100, 10).cuda()
+    g = torch.Generator().manual_seed(d * 1000 + B)
+    X = torch.randn(B, d, d, dtype=torch.complex64, generator=g) * (3.0 / d ** 0.5)
+    A = 0.5 * (X + X.transpose(1, 2).conj())
+    _, _, Gp = _eigh(pkg, A, params=P[3], vecs=False, fn=True)
+    G = _unpack(Gp, d)
+    w, U = torch.linalg.eigh(A.to(torch.complex128))
+    fw = net_oracle.eig_map(w.float(), net_oracle.layer_params(sd, 3)["g"]).to(torch.complex128)
+    Gt = (U * fw.unsqueeze(1)) @ U.transpose(1, 2).conj()
+    err = (G.to(torch.complex128) - Gt).abs().amax(dim=(1, 2)) / Gt.abs().amax(dim=(1, 2))
+    assert err.max() < 2e-5, (float(err.max()), int(err.argmax()))
+
+
 @pytest.mark.parametrize("tag", ["init_k10", "pert_k10", "pert_k5"])
 def test_forward_matches_reference_golden(pkg, tag):
     z, sd = load_net_case(tag)
@@ -526,11 +550,12 @@ def test_admmnet_full_module_matches_reference_golden(pkg):
     np.testing.assert_allclose(t3.cpu().numpy(), z["tau"][:5], atol=2e-6, rtol=1e-5)
 
 
-@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILP", "ADMMNET_LANES"])
+@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILTC", "ADMMNET_LANES"])
 def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
     """Every fast path has a plain sibling behind an environment switch (read once per process, hence the
     subprocess): ADMMNET_ARROW=0 dense eigen-solver at layer 0 instead of the arrowhead shortcut, ADMMNET_ROTF=0
-    one sweep at a time in the rotation kernel, ADMMNET_TAILP=0 non-persistent back-transformation,
+    one sweep at a time in the rotation kernel, ADMMNET_TAILTC=0 the SIMT (FFMA2) back-transformation and rebuild
+    instead of the tcgen05 kernel,
     ADMMNET_LANES=0 single stream.  Same inputs, same answer."""
     import subprocess
     import sys

@@ -6,7 +6,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-A_TMEM, A_NEG, A_MN, B_MN, TMA, SPLIT3 = 1, 2, 4, 8, 16, 32
+A_TMEM, A_NEG, A_MN, B_MN, TMA, SPLIT3, DCOL8 = 1, 2, 4, 8, 16, 32, 64
 
 
 def _tf32(x):
@@ -29,9 +29,9 @@ def _probe(A, B, D0, flags):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("flags", [0, A_NEG, A_TMEM, A_TMEM | A_NEG, TMA, A_MN, B_MN, A_MN | B_MN],
-                         ids=["ss", "ss_neg", "ts", "ts_neg", "tma", "a_mn", "b_mn", "ab_mn"])
-@pytest.mark.parametrize("N,K", [(112, 32), (104, 32), (208, 16), (32, 64)])
+@pytest.mark.parametrize("flags", [0, A_NEG, A_TMEM, A_TMEM | A_NEG, TMA, A_TMEM | DCOL8],
+                         ids=["ss", "ss_neg", "ts", "ts_neg", "tma", "ts_dcol8"])
+@pytest.mark.parametrize("N,K", [(112, 32), (104, 32), (208, 16), (48, 64), (64, 24)])
 def test_tf32_tile_exact_inputs(flags, N, K):
     rng = np.random.default_rng(N * 100 + K + flags)
     A = _tf32(rng.normal(size=(128, K)))
