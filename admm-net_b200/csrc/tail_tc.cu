@@ -253,30 +253,58 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
                     }
                 }
             }
-            // column groups of 8: real plane g -> columns 8g.., imaginary plane -> reversed columns
+            // column groups of 8: real plane g -> columns 8g.., imaginary plane -> reversed columns.  Groups that do not
+            // reach the locally transformed coordinates take the fast path (two 128-bit loads / plain zeros).
             const int ngr = dp / 8;
             for (int g = hh; g < 2 * ngr; g += 2) {
                 uint32_t vh[8], vl[8];
                 const bool im = g >= ngr;
+                const int amax = im ? (DP2 - 1 - 8 * g) : (8 * g + 7);        // largest coordinate in the group
+                if (pl.nloc == 0 || amax < aL) {
+                    if (im) {
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int acol = im ? (DP2 - 1 - (8 * g + jj)) : (8 * g + jj);      // coordinate of TMEM column 8g+jj
-                    float x = 0.f;
-                    if (row < d && acol < d) {
-                        if (acol >= aL) {
-                            // local-reflector coordinates: registers (static index through the unrolled select)
-                            float xr = 0.f, xi = 0.f;
+                        for (int jj = 0; jj < 8; ++jj) { vh[jj] = 0u; vl[jj] = 0u; }
+                    } else {
+                        float x[8];
+                        if (row < d) {
+                            const float4 z0 = *reinterpret_cast<const float4*>(Zt + row * ldz + 8 * g);
+                            const float4 z1 = (8 * g + 4 < ldz) ? *reinterpret_cast<const float4*>(Zt + row * ldz + 8 * g + 4)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                            x[0] = z0.x; x[1] = z0.y; x[2] = z0.z; x[3] = z0.w;
+                            x[4] = z1.x; x[5] = z1.y; x[6] = z1.z; x[7] = z1.w;
+                        } else {
 #pragma unroll
-                            for (int e = 0; e < TC_LOCAL_MAX; ++e)
-                                if (acol - aL == e) { xr = ur[e]; xi = ui[e]; }
-                            x = im ? xi : xr;
-                        } else if (!im) {
-                            x = Zt[row * ldz + acol];
+                            for (int jj = 0; jj < 8; ++jj) x[jj] = 0.f;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float xv = (8 * g + jj < d) ? x[jj] : 0.f;   // pad columns of the box are zero anyway
+                            const float h = rna_tf32(xv);
+                            vh[jj] = __float_as_uint(h);
+                            vl[jj] = __float_as_uint(xv - h);
                         }
                     }
-                    const float h = rna_tf32(x);
-                    vh[jj] = __float_as_uint(h);
-                    vl[jj] = __float_as_uint(x - h);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int acol = im ? (DP2 - 1 - (8 * g + jj)) : (8 * g + jj);      // coordinate of TMEM column 8g+jj
+                        float x = 0.f;
+                        if (row < d && acol < d) {
+                            if (acol >= aL) {
+                                // local-reflector coordinates: registers (static index through the unrolled select)
+                                float xr = 0.f, xi = 0.f;
+#pragma unroll
+                                for (int e = 0; e < TC_LOCAL_MAX; ++e)
+                                    if (acol - aL == e) { xr = ur[e]; xi = ui[e]; }
+                                x = im ? xi : xr;
+                            } else if (!im) {
+                                x = Zt[row * ldz + acol];
+                            }
+                        }
+                        const float h = rna_tf32(x);
+                        vh[jj] = __float_as_uint(h);
+                        vl[jj] = __float_as_uint(x - h);
+                    }
                 }
                 tc::tmem_st8(tXhi + lane_off + 8 * g, vh);
                 tc::tmem_st8(tXlo + lane_off + 8 * g, vl);
@@ -285,30 +313,88 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
 
         TC_MARK(TCP_S1)
         // ================= S2: Gram matrices and Y = V T for all blocks (SIMT) =================
-        for (int p = tid; p < pl.nblk * TC_NB * TC_NB; p += TC_NT) {
-            const int j = p / (TC_NB * TC_NB), c1 = (p / TC_NB) % TC_NB, c2 = p % TC_NB;
-            float2 acc = make_float2(0.f, 0.f);
-            if (c1 < c2 && c2 < pl.nb[j]) {
-                const int ka = pl.k0[j] + c1, kb = pl.k0[j] + c2;
-                const float2* va = Vs + voff(ka, d) - (ka + 1);
-                const float2* vb2 = Vs + voff(kb, d) - (kb + 1);
-                float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
-                int r = kb + 1;
-                for (; r + 1 < d; r += 2) {
-                    const float2 x0 = va[r], y0 = vb2[r], x1 = va[r + 1], y1 = vb2[r + 1];
-                    ax = fmaf(x0.x, y0.x, ax); ax = fmaf(x0.y, y0.y, ax);
-                    ay = fmaf(x0.x, y0.y, ay); ay = fmaf(-x0.y, y0.x, ay);
-                    bx = fmaf(x1.x, y1.x, bx); bx = fmaf(x1.y, y1.y, bx);
-                    by = fmaf(x1.x, y1.y, by); by = fmaf(-x1.y, y1.x, by);
-                }
-                if (r < d) {
-                    const float2 x0 = va[r], y0 = vb2[r];
-                    ax = fmaf(x0.x, y0.x, ax); ax = fmaf(x0.y, y0.y, ax);
-                    ay = fmaf(x0.x, y0.y, ay); ay = fmaf(-x0.y, y0.x, ay);
-                }
-                acc = make_float2(ax + bx, ay + by);                       // conj(v_c1) . v_c2
+        // S_j[c1][c2] = v_c1^H v_c2 for c1 < c2.  One item = (block, pair of rows c1 = 2p, 2p+1, strip of four columns
+        // c2 = 4s..4s+3) with 4s+3 > 2p: 42 items per block, each a 2x4 register tile (6 loads for 8 complex MACs per
+        // coordinate), packed FFMA2:  conj(a) b = a.x*(b.x,b.y) + a.y*(b.y,-b.x)  kept as P += a.x*b, Q += a.y*b.
+        for (int item = tid; item < pl.nblk * 42; item += TC_NT) {
+            const int j = item / 42;
+            int rem_i = item - j * 42, p2 = 0;
+            for (;; ++p2) {
+                const int cnt = 6 - ((2 * p2 + 1) >> 2);
+                if (rem_i < cnt) break;
+                rem_i -= cnt;
             }
-            Sg[p] = acc;
+            const int s4 = ((2 * p2 + 1) >> 2) + rem_i;                    // strip index
+            const int k0 = pl.k0[j], nbj = pl.nb[j];
+            const int c1 = 2 * p2, c2 = 4 * s4;
+            const float2* va0 = Vs + voff(k0 + c1, d) - (k0 + c1 + 1);
+            const float2* va1 = Vs + voff(k0 + c1 + 1, d) - (k0 + c1 + 2);
+            const float2* vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) vb[u] = Vs + voff(k0 + c2 + u, d) - (k0 + c2 + u + 1);
+            f32x2 Pa[2][4], Qa[2][4];
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { Pa[t][u] = pk2(0.f, 0.f); Qa[t][u] = pk2(0.f, 0.f); }
+            const int rfull = k0 + c2 + 4;                                 // from here on all four columns are stored
+            if (c2 + 3 < nbj && rfull <= d) {                              // (padded blocks take the generic path below)
+                // the three leading rows: column c2+u exists for r >= k0+c2+u+1
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const int r = k0 + c2 + 1 + e;
+                    if (r < d) {
+                        const float2 a0 = (r > k0 + c1) ? va0[r] : make_float2(0.f, 0.f);
+                        const float2 a1 = (r > k0 + c1 + 1) ? va1[r] : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            if (u <= e) {
+                                const float2 b = vb[u][r];
+                                const f32x2 bp = pk2(b.x, b.y);
+                                Pa[0][u] = fma2(bc2(a0.x), bp, Pa[0][u]); Qa[0][u] = fma2(bc2(a0.y), bp, Qa[0][u]);
+                                Pa[1][u] = fma2(bc2(a1.x), bp, Pa[1][u]); Qa[1][u] = fma2(bc2(a1.y), bp, Qa[1][u]);
+                            }
+                        }
+                    }
+                }
+                for (int r = rfull; r < d; ++r) {
+                    const float2 a0 = va0[r], a1 = va1[r];
+                    const f32x2 a0x = bc2(a0.x), a0y = bc2(a0.y), a1x = bc2(a1.x), a1y = bc2(a1.y);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 b = vb[u][r];
+                        const f32x2 bp = pk2(b.x, b.y);
+                        Pa[0][u] = fma2(a0x, bp, Pa[0][u]); Qa[0][u] = fma2(a0y, bp, Qa[0][u]);
+                        Pa[1][u] = fma2(a1x, bp, Pa[1][u]); Qa[1][u] = fma2(a1y, bp, Qa[1][u]);
+                    }
+                }
+            } else {
+                for (int r = k0 + c2 + 1; r < d; ++r) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int ca = c1 + t;
+                        if (ca >= nbj || r <= k0 + ca) continue;
+                        const float2 av = (t ? va1 : va0)[r];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (c2 + u >= nbj || r <= k0 + c2 + u) continue;
+                            const float2 b = vb[u][r];
+                            const f32x2 bp = pk2(b.x, b.y);
+                            Pa[t][u] = fma2(bc2(av.x), bp, Pa[t][u]); Qa[t][u] = fma2(bc2(av.y), bp, Qa[t][u]);
+                        }
+                    }
+                }
+            }
+            float2* S = Sg + j * TC_NB * TC_NB;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 pp = upk2(Pa[t][u]), qq = upk2(Qa[t][u]);
+                    // conj(a) b = (a.x b.x + a.y b.y, a.x b.y - a.y b.x)
+                    const bool live = (c1 + t < c2 + u) && (c2 + u < nbj);
+                    S[(c1 + t) * TC_NB + c2 + u] = live ? make_float2(pp.x + qq.y, pp.y - qq.x) : make_float2(0.f, 0.f);
+                }
         }
         __syncthreads();
         TC_MARK(TCP_GRAM)
@@ -330,18 +416,19 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
                     tk = taus[k];
                     if (arow > k) v = Vs[voff(k, d) - (k + 1) + arow];
                 }
-                float sx0 = v.x, sy0 = v.y, sx1 = 0.f, sy1 = 0.f;
+                // v - sum_m y_m S[m][c]:  y s = y.x*(s.x,s.y) + y.y*(-s.y,s.x), kept as P += y.x*s, Q += y.y*s (two
+                // independent chains each by the parity of m), packed FFMA2
+                f32x2 P0 = pk2(0.f, 0.f), Q0 = pk2(0.f, 0.f), P1 = pk2(0.f, 0.f), Q1 = pk2(0.f, 0.f);
 #pragma unroll
                 for (int m = 0; m < c; ++m) {
                     const float2 s = S[m * TC_NB + c];
-                    if (m & 1) {
-                        sx1 = fmaf(-y[m].x, s.x, sx1); sx1 = fmaf(y[m].y, s.y, sx1);
-                        sy1 = fmaf(-y[m].x, s.y, sy1); sy1 = fmaf(-y[m].y, s.x, sy1);
-                    } else {
-                        sx0 = fmaf(-y[m].x, s.x, sx0); sx0 = fmaf(y[m].y, s.y, sx0);
-                        sy0 = fmaf(-y[m].x, s.y, sy0); sy0 = fmaf(-y[m].y, s.x, sy0);
-                    }
+                    const f32x2 sp = pk2(s.x, s.y);
+                    if (m & 1) { P1 = fma2(bc2(y[m].x), sp, P1); Q1 = fma2(bc2(y[m].y), sp, Q1); }
+                    else       { P0 = fma2(bc2(y[m].x), sp, P0); Q0 = fma2(bc2(y[m].y), sp, Q0); }
                 }
+                const float2 p0 = upk2(P0), q0 = upk2(Q0), p1 = upk2(P1), q1 = upk2(Q1);
+                const float sx0 = v.x - ((p0.x + p1.x) - (q0.y + q1.y)), sy0 = v.y - ((p0.y + p1.y) + (q0.x + q1.x));
+                const float sx1 = 0.f, sy1 = 0.f;
                 y[c] = cmul(tk, make_float2(sx0 + sx1, sy0 + sy1));
             }
             float4* dst = reinterpret_cast<float4*>(Yall + (size_t)item * TC_NB);
@@ -358,8 +445,10 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
             float* Vhi = tiles;
             float* Vlo = tiles + 48 * K2;
             // ---- V tiles: rows rho < 24: [Vr(a) | Vi(rev a)], rows 24..47: [-Vi(a) | Vr(rev a)], K-major, LBO = 48*16
-            for (int idx = tid; idx < TC_NB * Na; idx += TC_NT) {
-                const int c = idx % TC_NB, ar = idx / TC_NB, acol = a0 + ar, k = k0 + c;
+            // lane -> (c & 7, coordinate & 3): the 32 stores of a warp fall into 32 different banks
+            for (int it = warp; it < 3 * (Na / 4); it += TC_NT / 32) {
+                const int chi = it % 3, ag = it / 3;
+                const int c = 8 * chi + (lane >> 2), ar = 4 * ag + (lane & 3), acol = a0 + ar, k = k0 + c;
                 float2 v = make_float2(0.f, 0.f);
                 if (c < nbj && acol > k && acol < d) v = Vs[voff(k, d) - (k + 1) + acol];
                 const int k1 = ar, k2 = K2 - 1 - ar;
@@ -383,16 +472,11 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
             // ---- GEMM 1: [Pr | Pi] = X(window) * Vtile^T, 3 split terms
             if (tid == 0) {
                 const uint32_t idesc = tc::idesc_tf32(128, 48);
-                const uint32_t vhi = tc::smem_u32(Vhi), vlo = tc::smem_u32(Vlo);
-                uint32_t acc = 0;
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t xa = (term == 2 ? tXlo : tXhi) + a0;
-                    const uint32_t vb = term == 1 ? vlo : vhi;
-                    for (int ks = 0; ks < K2 / 8; ++ks) {
-                        tc::mma_tf32_ts(tP, xa + 8 * ks, tc::smem_desc(vb + ks * 2 * 768, 768, 128), idesc, acc);
-                        acc = 1;
-                    }
-                }
+                const uint64_t vhi = tc::smem_desc(tc::smem_u32(Vhi), 768, 128), vlo = tc::smem_desc(tc::smem_u32(Vlo), 768, 128);
+                const int nks = K2 / 8;
+                tc::mma_chain_ts(tP, tXhi + a0, vhi, 96, nks, idesc, 0u);      // hi * hi
+                tc::mma_chain_ts(tP, tXhi + a0, vlo, 96, nks, idesc, 1u);      // hi * lo
+                tc::mma_chain_ts(tP, tXlo + a0, vhi, 96, nks, idesc, 1u);      // lo * hi
                 tc::mma_commit(bar_mma);
             }
             wait_mma();
@@ -418,8 +502,9 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
             float* YPr_lo = tiles + 6 * K2 * 4;
             float* YPi_hi = tiles + 2 * 6 * K2 * 4;
             float* YPi_lo = tiles + 3 * 6 * K2 * 4;
-            for (int idx = tid; idx < TC_NB * Na; idx += TC_NT) {
-                const int c = idx % TC_NB, ar = idx / TC_NB, acol = a0 + ar;
+            for (int it = warp; it < 6 * (Na / 8); it += TC_NT / 32) {
+                const int chi = it % 6, ag = it / 6;
+                const int c = 4 * chi + (lane & 3), ar = 8 * ag + (lane >> 2), acol = a0 + ar;
                 float2 yv = make_float2(0.f, 0.f);
                 if (acol > k0 && acol < d) yv = Yall[(size_t)(pl.yoff[j] + acol - (k0 + 1)) * TC_NB + c];
                 const int n1 = ar, n2 = K2 - 1 - ar;
@@ -436,41 +521,65 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
             // ---- GEMM 2: X_lo(window) += Pr * YPr^T + Pi * YPi^T, 3 split terms each
             if (tid == 0) {
                 const uint32_t idesc = tc::idesc_tf32(128, K2);
-                const uint32_t lbo = (uint32_t)K2 * 16;
-                const uint32_t yb[4] = {tc::smem_u32(YPr_hi), tc::smem_u32(YPr_lo), tc::smem_u32(YPi_hi), tc::smem_u32(YPi_lo)};
-                for (int part = 0; part < 2; ++part) {        // A = Pr, Pi
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t pa = tP + (term == 2 ? 48 : 0) + part * TC_NB;
-                        const uint32_t tb = yb[2 * part + (term == 1 ? 1 : 0)];
-                        for (int ks = 0; ks < TC_NB / 8; ++ks)
-                            tc::mma_tf32_ts(tXlo + a0, pa + 8 * ks, tc::smem_desc(tb + ks * 2 * lbo, lbo, 128), idesc, 1);
-                    }
-                }
+                const uint32_t lbo = (uint32_t)K2 * 16, step = 2 * lbo / 16;
+                const uint64_t yprh = tc::smem_desc(tc::smem_u32(YPr_hi), lbo, 128), yprl = tc::smem_desc(tc::smem_u32(YPr_lo), lbo, 128);
+                const uint64_t ypih = tc::smem_desc(tc::smem_u32(YPi_hi), lbo, 128), ypil = tc::smem_desc(tc::smem_u32(YPi_lo), lbo, 128);
+                const uint32_t dw = tXlo + a0;
+                tc::mma_chain_ts(dw, tP, yprh, step, TC_NB / 8, idesc, 1u);                 // Pr_hi * YPr_hi
+                tc::mma_chain_ts(dw, tP, yprl, step, TC_NB / 8, idesc, 1u);                 // Pr_hi * YPr_lo
+                tc::mma_chain_ts(dw, tP + 48, yprh, step, TC_NB / 8, idesc, 1u);            // Pr_lo * YPr_hi
+                tc::mma_chain_ts(dw, tP + TC_NB, ypih, step, TC_NB / 8, idesc, 1u);         // Pi_hi * YPi_hi
+                tc::mma_chain_ts(dw, tP + TC_NB, ypil, step, TC_NB / 8, idesc, 1u);         // Pi_hi * YPi_lo
+                tc::mma_chain_ts(dw, tP + 48 + TC_NB, ypih, step, TC_NB / 8, idesc, 1u);    // Pi_lo * YPi_hi
                 tc::mma_commit(bar_mma);
             }
             wait_mma();
             TC_MARK(TCP_GEMM2)
             // ---- re-split the window: x = hi + lo, hi' = rna(x), lo' = x - hi'   (last block: done by the W staging)
             if (j > 0) {
-                for (int g = a0 / 8 + hh; g < (DP2 - a0) / 8; g += 2) {
-                    uint32_t vh[8], vl[8];
-                    tc::tmem_ld8(tXhi + lane_off + 8 * g, vh);
-                    tc::tmem_ld8(tXlo + lane_off + 8 * g, vl);
+                // two register sets: the loads of the next column group are in flight while this one is re-split
+                const int g0 = a0 / 8 + hh, g1 = (DP2 - a0) / 8;
+                uint32_t ah[8], al[8], bh[8], bl[8];
+                if (g0 < g1) {
+                    tc::tmem_ld8(tXhi + lane_off + 8 * g0, ah);
+                    tc::tmem_ld8(tXlo + lane_off + 8 * g0, al);
+                }
+                for (int g = g0; g < g1; g += 4) {
                     tc::tmem_wait_ld();
+                    if (g + 2 < g1) {
+                        tc::tmem_ld8(tXhi + lane_off + 8 * (g + 2), bh);
+                        tc::tmem_ld8(tXlo + lane_off + 8 * (g + 2), bl);
+                    }
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) {
-                        const float x = __uint_as_float(vh[jj]) + __uint_as_float(vl[jj]);
+                        const float x = __uint_as_float(ah[jj]) + __uint_as_float(al[jj]);
                         const float h = rna_tf32(x);
-                        vh[jj] = __float_as_uint(h);
-                        vl[jj] = __float_as_uint(x - h);
+                        ah[jj] = __float_as_uint(h);
+                        al[jj] = __float_as_uint(x - h);
                     }
-                    tc::tmem_st8(tXhi + lane_off + 8 * g, vh);
-                    tc::tmem_st8(tXlo + lane_off + 8 * g, vl);
+                    tc::tmem_st8(tXhi + lane_off + 8 * g, ah);
+                    tc::tmem_st8(tXlo + lane_off + 8 * g, al);
+                    if (g + 2 < g1) {
+                        tc::tmem_wait_ld();
+                        if (g + 4 < g1) {
+                            tc::tmem_ld8(tXhi + lane_off + 8 * (g + 4), ah);
+                            tc::tmem_ld8(tXlo + lane_off + 8 * (g + 4), al);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float x = __uint_as_float(bh[jj]) + __uint_as_float(bl[jj]);
+                            const float h = rna_tf32(x);
+                            bh[jj] = __float_as_uint(h);
+                            bl[jj] = __float_as_uint(x - h);
+                        }
+                        tc::tmem_st8(tXhi + lane_off + 8 * (g + 2), bh);
+                        tc::tmem_st8(tXlo + lane_off + 8 * (g + 2), bl);
+                    }
                 }
             }
+            TC_MARK(TCP_RESPLIT)
         }
 
-        TC_MARK(TCP_RESPLIT)
         // ================= rebuild: W tiles, G = W W^H on the tensor cores =================
         {
             const int lbw = pl.lbo_w / 4;                                      // floats per K chunk
@@ -478,12 +587,9 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
             float* Wt = tiles;                                                 // Wr_hi, Wr_lo, Wi_hi, Wi_lo
             const int ngr = dp / 8;
             const int kbase = (row >> 2) * lbw + (row & 3);
-            // (tcgen05.ld is warp-collective: every lane takes part, only the shared-memory stores are predicated)
-            for (int g = hh; g < 2 * ngr; g += 2) {
-                uint32_t vh[8], vl[8];
-                tc::tmem_ld8(tXhi + lane_off + 8 * g, vh);
-                tc::tmem_ld8(tXlo + lane_off + 8 * g, vl);
-                tc::tmem_wait_ld();
+            // (tcgen05.ld is warp-collective: every lane takes part, only the shared-memory stores are predicated;
+            //  two register sets keep the next group's loads in flight while this one is scaled, split and stored)
+            auto stage_group = [&](int g, const uint32_t (&vh)[8], const uint32_t (&vl)[8]) {
                 const bool im = g >= ngr;
                 float* Th = Wt + (im ? 2 * tsz : 0);
                 float* Tl = Th + tsz;
@@ -497,28 +603,52 @@ __global__ void __launch_bounds__(TC_NT, 1) k_tail_tc(TailTcArgs a, const __grid
                         Tl[kbase + acol * 4] = w - h;
                     }
                 }
+            };
+            {
+                uint32_t ah[8], al[8], bh[8], bl[8];
+                const int g1 = 2 * ngr;
+                tc::tmem_ld8(tXhi + lane_off + 8 * hh, ah);
+                tc::tmem_ld8(tXlo + lane_off + 8 * hh, al);
+                for (int g = hh; g < g1; g += 4) {
+                    tc::tmem_wait_ld();
+                    if (g + 2 < g1) {
+                        tc::tmem_ld8(tXhi + lane_off + 8 * (g + 2), bh);
+                        tc::tmem_ld8(tXlo + lane_off + 8 * (g + 2), bl);
+                    }
+                    stage_group(g, ah, al);
+                    if (g + 2 < g1) {
+                        tc::tmem_wait_ld();
+                        if (g + 4 < g1) {
+                            tc::tmem_ld8(tXhi + lane_off + 8 * (g + 4), ah);
+                            tc::tmem_ld8(tXlo + lane_off + 8 * (g + 4), al);
+                        }
+                        stage_group(g + 2, bh, bl);
+                    }
+                }
             }
             publish();
             TC_MARK(TCP_WSTAGE)
             if (tid == 0) {
-                const uint32_t w0 = tc::smem_u32(Wt);
-                const uint32_t tb[4] = {w0, w0 + (uint32_t)tsz * 4, w0 + 2u * tsz * 4, w0 + 3u * tsz * 4};   // rh rl ih il
-                const uint32_t lbo = (uint32_t)pl.lbo_w;
-                // G_r (columns [0,dp)) = Wr Wr^T + Wi Wi^T ; G_i (columns [dp,2dp)) = Wi Wr^T - Wr Wi^T
-                for (int prod = 0; prod < 4; ++prod) {
-                    const int ap = (prod == 0 || prod == 3) ? 0 : 1;           // A plane: r, i, i, r
-                    const int bp = (prod == 0 || prod == 2) ? 0 : 1;           // B plane: r, i, r, i
-                    const uint32_t dcol = tbase + (prod >= 2 ? dp : 0);
-                    const uint32_t idesc = tc::idesc_tf32(128, dp, prod == 3 ? 1 : 0);
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t ta = tb[2 * ap + (term == 2 ? 1 : 0)], tbb = tb[2 * bp + (term == 1 ? 1 : 0)];
-                        for (int ks = 0; ks < dp / 8; ++ks) {
-                            const uint32_t acc = (prod == 0 || prod == 2) ? ((term | ks) ? 1u : 0u) : 1u;
-                            tc::mma_tf32_ss(dcol, tc::smem_desc(ta + ks * 2 * lbo, lbo, 128),
-                                            tc::smem_desc(tbb + ks * 2 * lbo, lbo, 128), idesc, acc);
-                        }
-                    }
-                }
+                const uint32_t w0 = tc::smem_u32(Wt), lbo = (uint32_t)pl.lbo_w, step = 2 * lbo / 16;
+                uint64_t tb[4];                                                 // Wr_hi, Wr_lo, Wi_hi, Wi_lo
+#pragma unroll
+                for (int t = 0; t < 4; ++t) tb[t] = tc::smem_desc(w0 + (uint32_t)t * tsz * 4, lbo, 128);
+                const uint32_t id = tc::idesc_tf32(128, dp), idn = tc::idesc_tf32(128, dp, 1);
+                const int nks = dp / 8;
+                const uint32_t gr = tbase, gi = tbase + dp;
+                // G_r (columns [0,dp)) = Wr Wr^T + Wi Wi^T ; G_i (columns [dp,2dp)) = Wi Wr^T - Wr Wi^T ; 3 split terms each
+                tc::mma_chain_ss(gr, tb[0], step, tb[0], step, nks, id, 0u);
+                tc::mma_chain_ss(gr, tb[0], step, tb[1], step, nks, id, 1u);
+                tc::mma_chain_ss(gr, tb[1], step, tb[0], step, nks, id, 1u);
+                tc::mma_chain_ss(gr, tb[2], step, tb[2], step, nks, id, 1u);
+                tc::mma_chain_ss(gr, tb[2], step, tb[3], step, nks, id, 1u);
+                tc::mma_chain_ss(gr, tb[3], step, tb[2], step, nks, id, 1u);
+                tc::mma_chain_ss(gi, tb[2], step, tb[0], step, nks, id, 0u);
+                tc::mma_chain_ss(gi, tb[2], step, tb[1], step, nks, id, 1u);
+                tc::mma_chain_ss(gi, tb[3], step, tb[0], step, nks, id, 1u);
+                tc::mma_chain_ss(gi, tb[0], step, tb[2], step, nks, idn, 1u);
+                tc::mma_chain_ss(gi, tb[0], step, tb[3], step, nks, idn, 1u);
+                tc::mma_chain_ss(gi, tb[1], step, tb[2], step, nks, idn, 1u);
                 tc::mma_commit(bar_mma);
             }
             wait_mma();

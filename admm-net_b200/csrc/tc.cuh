@@ -130,6 +130,29 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Chains of `n` MMAs over consecutive K = 8 steps: the A operand advances by 8 TMEM columns (or by a_step16 16-byte
+// units in shared memory), B by b_step16.  Descriptors are advanced with one 64-bit add (only the 14-bit address
+// field changes: shared memory is < 256 KB), so the single issuing thread spends ~6 instructions per MMA.
+__device__ __forceinline__ void mma_chain_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t b_step16,
+                                             int n, uint32_t idesc, uint32_t first_accumulate) {
+    mma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, first_accumulate);
+#pragma unroll 4
+    for (int ks = 1; ks < n; ++ks) {
+        a_tmem += 8;
+        b_desc += b_step16;
+        mma_tf32_ts(d_tmem, a_tmem, b_desc, idesc, 1u);
+    }
+}
+__device__ __forceinline__ void mma_chain_ss(uint32_t d_tmem, uint64_t a_desc, uint32_t a_step16, uint64_t b_desc,
+                                             uint32_t b_step16, int n, uint32_t idesc, uint32_t first_accumulate) {
+    mma_tf32_ss(d_tmem, a_desc, b_desc, idesc, first_accumulate);
+#pragma unroll 4
+    for (int ks = 1; ks < n; ++ks) {
+        a_desc += a_step16;
+        b_desc += b_step16;
+        mma_tf32_ss(d_tmem, a_desc, b_desc, idesc, 1u);
+    }
+}
 // all MMAs issued so far by this thread -> one arrival on the mbarrier when they have completed
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
