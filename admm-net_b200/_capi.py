@@ -26,6 +26,7 @@ _PROTOS = {
     "admm_classic_forward": (_i, [_vp, _vp, _i, _i, _i, _d, _i, _vp, _vp]),
     "peak_search_full": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _d, _d, _i, _i, _vp, _vp, _i,
                               _vp, _vp, _vp, _vp]),
+    "peak_surface_maxima": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "peak_search_points": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "admmnet_head_param_count": (_i, [_i, _i]),
     "admmnet_peak_head": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -19,8 +19,25 @@ from . import _capi
 EPS = 1e-8
 
 
+_STATUS = {}          # device -> int32[1]: sticky OR of the eigen-solver status words of every BatchedEigh call
+
+
+def eigh_status(device=None, reset=True):
+    """Status accumulated by BatchedEigh since the last reset (one device->host read; 0 = every solve converged).
+    The training step checks it once per step instead of synchronising inside every layer."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    st = _STATUS.get(str(dev))
+    if st is None:
+        return 0
+    v = int(st.item())
+    if reset and v:
+        st.zero_()
+    return v
+
+
 class BatchedEigh(torch.autograd.Function):
-    """(values fp32 [B,d], vectors c64 [B,d,d]) of Hermitian c64 [B,d,d]; vectors carry no gradient."""
+    """(values fp32 [B,d], vectors c64 [B,d,d]) of Hermitian c64 [B,d,d]; vectors carry no gradient.
+    No host synchronisation (CUDA-graph capturable): convergence is reported through eigh_status()."""
 
     @staticmethod
     def forward(ctx, A):
@@ -35,12 +52,14 @@ class BatchedEigh(torch.autograd.Function):
         ws = torch.empty(nb.value, dtype=torch.uint8, device=A.device)
         vals = torch.empty(B, d, dtype=torch.float32, device=A.device)
         vecs = torch.empty(B, d, d, dtype=torch.complex64, device=A.device)
-        status = torch.zeros(1, dtype=torch.int32, device=A.device)
-        _capi.check(L.admmnet_eigh_batched(A.data_ptr(), B, d, vals.data_ptr(), vecs.data_ptr(), None, None,
-                                           ws.data_ptr(), nb.value, 0,
-                                           torch.cuda.current_stream(A.device).cuda_stream, status.data_ptr()))
-        if int(status.item()):
-            raise _capi.AdmmnetError("eigen-solver did not converge")
+        key = str(A.device)
+        if key not in _STATUS:
+            _STATUS[key] = torch.zeros(1, dtype=torch.int32, device=A.device)
+        status = _STATUS[key]                      # the kernels only ever OR bits into it
+        with torch.cuda.device(A.device):
+            _capi.check(L.admmnet_eigh_batched(A.data_ptr(), B, d, vals.data_ptr(), vecs.data_ptr(), None, None,
+                                               ws.data_ptr(), nb.value, 0,
+                                               torch.cuda.current_stream(A.device).cuda_stream, status.data_ptr()))
         ctx.save_for_backward(vecs)
         ctx.mark_non_differentiable(vecs)
         return vals, vecs
@@ -59,7 +78,9 @@ def _block(phi, h, c):
     """[[diag(h), phi],[phi^H, c]]  (admm_net.py:273-284 / 428-439)."""
     B = phi.shape[0]
     H = torch.diag_embed(h)
-    corner = torch.full((B, 1, 1), c, device=h.device, dtype=h.dtype)
+    # c: the reference's `.item()` scalar, kept as a detached 0-dim device tensor (same fp32 value, no gradient, no
+    # host synchronisation)
+    corner = (c if torch.is_tensor(c) else torch.tensor(c, device=h.device)).to(h.dtype).reshape(1, 1, 1).expand(B, 1, 1)
     top = torch.cat([H, phi.unsqueeze(-1)], dim=2)
     bottom = torch.cat([phi.conj().unsqueeze(1), corner], dim=2)
     return torch.cat([top, bottom], dim=1)
@@ -92,7 +113,7 @@ def forward_train(model, y, b, sigma, _eigh=None):
         cv = Asig * tc.abs().max(dim=1, keepdim=True)[0] + tc.sum(dim=1, keepdim=True)
         h = tc * torch.clamp(torch.sigmoid(hl.projection_weight) / (cv + EPS), max=1.0)
         # ---- GLayer
-        c0 = (1.0 / (F.softplus(gl.lambda_param) ** 2 + EPS)).item()
+        c0 = (1.0 / (F.softplus(gl.lambda_param) ** 2 + EPS)).detach()          # `.item()` in admm_net.py:269-271
         A = _block(phi, h, c0) - (1.0 / (F.softplus(gl.rho) + EPS)) * Z
         A = 0.5 * (A + A.transpose(1, 2).conj())
         vals, vecs = eigh(A)
@@ -101,11 +122,11 @@ def forward_train(model, y, b, sigma, _eigh=None):
         Gn = vecs @ (lam.to(torch.complex64).unsqueeze(-1) * vecs.transpose(1, 2).conj())
         G = 0.5 * (Gn + Gn.transpose(1, 2).conj())
         # ---- ZLayer
-        c1 = (1.0 / (F.softplus(zl.lambda_param) ** 2 + EPS)).item()
+        c1 = (1.0 / (F.softplus(zl.lambda_param) ** 2 + EPS)).detach()          # `.item()` in admm_net.py:424-426
         R = G - _block(phi, h, c1)
         rho_z = F.softplus(zl.rho)
         r = torch.norm(R, dim=[1, 2], p="fro")
-        feats = torch.stack([torch.full((B,), k / 10.0, device=dev), torch.full((B,), rho_z.item(), device=dev),
+        feats = torch.stack([torch.full((B,), k / 10.0, device=dev), rho_z.detach().expand(B),     # `.item()`, :458
                              r / (r.mean() + EPS)], dim=1)
         alpha = rho_z * (0.5 + 1.5 * zl.residual_scale_net(feats)).squeeze(1)
         Z = Z + alpha.unsqueeze(-1).unsqueeze(-1) * R

@@ -17,12 +17,15 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in SRC + [HDR])
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    """debug=True adds -DADMMNET_DEBUG: in-kernel bounds asserts (csrc/common.cuh ADMM_ASSERT) that trap with file:line."""
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", os.path.join(HERE, "csrc", "capi.cu"), "-o", LIB]
+    if debug:
+        cmd.insert(1, "-DADMMNET_DEBUG")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -31,4 +34,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv or "--debug" in sys.argv, verbose=True, debug="--debug" in sys.argv)

@@ -32,6 +32,24 @@ static int fail(int code, const std::string& msg) {
             return fail(ADMMNET_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
     } while (0)
 
+// Dynamic shared-memory opt-in, raised monotonically per (device, kernel) under a mutex: two host threads launching
+// the same kernel with different footprints (k_head2's stages, two matrix orders) must never LOWER the limit between
+// the other thread's cudaFuncSetAttribute and its launch ("invalid argument" at launch).
+template <typename F>
+static cudaError_t ensure_smem(F* func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> cur;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    int& have = cur[std::make_pair(dev, (const void*)func)];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
 // ------------------------------------------------------------------------------------ profiling hooks
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
 // Process-global (guarded by a mutex); off by default (then the only cost is one branch per launch).
@@ -234,11 +252,11 @@ int launch_head2(const Ws& w, int B, int d, cudaStream_t st, const int* skip = n
         prof::Scope pscope(prof::HEAD2, st);
         if (dcur > 64) {
             const size_t sm = head2_smem_bytes<256, 128>(h.d2, h.ld2);
-            CK(cudaFuncSetAttribute(k_head2<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(ensure_smem(k_head2<256, 128>, (int)sm));
             k_head2<256, 128><<<B, 256, sm, st>>>(h);
         } else {
             const size_t sm = head2_smem_bytes<128, 64>(h.d2, h.ld2);
-            CK(cudaFuncSetAttribute(k_head2<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(ensure_smem(k_head2<128, 64>, (int)sm));
             k_head2<128, 64><<<B, 128, sm, st>>>(h);
         }
         CK(cudaGetLastError());
@@ -261,7 +279,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         cudaStream_t st_main = st;
         cudaStream_t st = side ? qst : st_main;
         const size_t sm = (size_t)2 * d * QL_THREADS * sizeof(double);
-        CK(cudaFuncSetAttribute(k_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(ensure_smem(k_ql, (int)sm));
         prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
                                                                          status, dc_tears(d, B), w.rho, skip);
@@ -273,11 +291,11 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
     }
     {
         const size_t sm = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (4 * ((d + 3) / 4)) * sizeof(float);
-        CK(cudaFuncSetAttribute(k_rot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(ensure_smem(k_rot, (int)sm));
         prof::Scope pscope(prof::ROT, st);
         static const bool fused = !(getenv("ADMMNET_ROTF") && atoi(getenv("ADMMNET_ROTF")) == 0);
         if (fused) {      // same shared-memory size: ring of 4 x 256 entries instead of 2 x 512
-            CK(cudaFuncSetAttribute(k_rotf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(ensure_smem(k_rotf, (int)sm));
             k_rotf<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
         } else
         k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
@@ -307,7 +325,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
                 ++m.nr;
             }
             const size_t smm = merge_smem_bytes(d);
-            CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm));
+            CK(ensure_smem(k_merge, (int)smm));
             prof::Scope pscope(prof::MERGE, st);
             k_merge<<<B, MG_THREADS, smm, st>>>(m);
             CK(cudaGetLastError());
@@ -335,8 +353,8 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
             int dev = 0, nsm = 0;
             CK(cudaGetDevice(&dev));
             CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-            CK(cudaFuncSetAttribute(k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.total));
-            k_tail_tc<<<B < nsm ? B : nsm, TC_NT, plan.total, st>>>(ta, tmZ);
+            CK(ensure_smem(k_tail_tc, plan.total));
+            k_tail_tc<<<B < nsm ? B : nsm, TC_THREADS, plan.total, st>>>(ta, tmZ);
             CK(cudaGetLastError());
             return 0;
         }
@@ -347,7 +365,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
             int dev = 0, nsm = 0;
             CK(cudaGetDevice(&dev));
             CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-            CK(cudaFuncSetAttribute(k_tail_p<13, 416, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp));
+            CK(ensure_smem(k_tail_p<13, 416, 8>, (int)smp));
             k_tail_p<13, 416, 8><<<B < nsm ? B : nsm, 416, smp, st>>>(t);
             CK(cudaGetLastError());
             return 0;
@@ -355,10 +373,10 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         const size_t sm = tail_smem_bytes(d, t.ldu);
         // (a 16-lane row split, k_tail<7, 832, 16>, doubles the warps per SM but measured 25 % slower)
         if (d <= 104) {
-            CK(cudaFuncSetAttribute(k_tail<13, 416, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(ensure_smem(k_tail<13, 416, 8>, (int)sm));
             k_tail<13, 416, 8><<<B, 416, sm, st>>>(t);
         } else {
-            CK(cudaFuncSetAttribute(k_tail<16, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(ensure_smem(k_tail<16, 512, 8>, (int)sm));
             k_tail<16, 512, 8><<<B, 512, sm, st>>>(t);
         }
         CK(cudaGetLastError());
@@ -488,7 +506,7 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
         aa.handled = w.handled; aa.lam_out = nullptr; aa.U_out = nullptr;
         aa.B = Bc; aa.n = n; aa.d = d; aa.ldu = 4 * ((d + 3) / 4);
         const size_t sma = arrow_smem_bytes(d, aa.ldu);
-        CK(cudaFuncSetAttribute(k_arrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+        CK(ensure_smem(k_arrow, (int)sma));
         prof::Scope pscope(prof::ARROW, st);
         k_arrow<<<Bc, AR_NT, sma, st>>>(aa);
         CK(cudaGetLastError());
@@ -496,7 +514,7 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     }
     h.skip = skip;
     const size_t sm = head_smem_bytes(d, h.ld);
-    CK(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(ensure_smem(k_head, (int)sm));
     {
         prof::Scope pscope(prof::HEAD, st);
         k_head<<<Bc, 256, sm, st>>>(h);
@@ -663,7 +681,7 @@ extern "C" int admmnet_arrow_eigh(const float* h, const void* phi, const float* 
     aa.handled = handled; aa.lam_out = evals; aa.U_out = (float2*)evecs;
     aa.B = B; aa.n = n; aa.d = n + 1; aa.ldu = 4 * ((n + 1 + 3) / 4);
     const size_t sma = arrow_smem_bytes(aa.d, aa.ldu);
-    CK(cudaFuncSetAttribute(k_arrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+    CK(ensure_smem(k_arrow, (int)sma));
     prof::Scope pscope(prof::ARROW, (cudaStream_t)stream);
     k_arrow<<<B, AR_NT, sma, (cudaStream_t)stream>>>(aa);
     CK(cudaGetLastError());
@@ -691,7 +709,7 @@ extern "C" int admmnet_eigh_batched(const void* A, int B, int d, float* evals, v
     cudaStream_t st = (cudaStream_t)stream;
     const int ld = d | 1;
     const size_t sm = head_smem_bytes(d, ld);
-    CK(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(ensure_smem(k_tridiag, (int)sm));
     k_tridiag<<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT, w.Ttr, stage1_steps(d));
     CK(cudaGetLastError());
     if (int e = launch_head2(w, B, d, st)) return e;
@@ -755,9 +773,32 @@ extern "C" int peak_search_full(const void* phi, int phi_is_c128, int B, int xba
     a.axis_x = axis_x; a.axis_y = axis_y; a.Gx = Gx; a.Gy = Gy;
     a.xmin = xmin; a.xmax = xmax; a.xstep = xstep; a.ymin = ymin; a.ymax = ymax; a.ystep = ystep;
     a.reducefactor = reducefactor; a.iters = iters; a.pmax = pmax; a.ptile = ptile; a.peaks = peaks; a.count = count;
-    a.topl = topl; a.top = top; a.surface = surface; a.status = status_dev;
-    CK(cudaFuncSetAttribute(k_peak_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    a.topl = topl; a.top = top; a.surface = surface; a.status = status_dev; a.surface_in = nullptr;
+    CK(ensure_smem(k_peak_search, (int)sm));
     prof::Scope pscope(prof::PEAK, (cudaStream_t)stream);
+    k_peak_search<<<B, PEAK_NT, sm, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Debug tap: the 8-connected, plateau-aware local-maximum stage of k_peak_search (skimage.morphology.local_maxima as
+// peakSearchUtils.py:118 calls it) on a caller-supplied surface; peaks[B][pmax][3] = (axis_x[ix], axis_y[iy], value)
+// in row-major discovery order (np.where order, peakSearchUtils.py:119).
+extern "C" int peak_surface_maxima(const double* surface, int B, const double* axis_x, int Gx, const double* axis_y,
+                                   int Gy, int pmax, double* peaks, int* count, int* status_dev, void* stream) {
+    if (!surface || !axis_x || !axis_y || !peaks || !count || !status_dev) return fail(ADMMNET_ERR_ARG, "null pointer");
+    if (B <= 0 || Gx <= 0 || Gy <= 0 || pmax <= 0) return fail(ADMMNET_ERR_ARG, "bad sizes");
+    const size_t sm0 = peak_smem_bytes(Gx, Gy, 1, 1, pmax);
+    const size_t per_peak = peak_refine_bytes_per_peak(1, 1);
+    if (sm0 + 4 * per_peak > 227 * 1024) return fail(ADMMNET_ERR_ARG, "surface too large for one CTA's shared memory");
+    PeakArgs a;
+    a.phi = surface; a.phi_is_c128 = 1; a.B = B; a.xb = 1; a.yb = 1;
+    a.axis_x = axis_x; a.axis_y = axis_y; a.Gx = Gx; a.Gy = Gy;
+    a.xmin = 0; a.xmax = 1; a.xstep = 1; a.ymin = 0; a.ymax = 1; a.ystep = 1;
+    a.reducefactor = 0.1; a.iters = 0; a.pmax = pmax; a.ptile = 4; a.peaks = peaks; a.count = count;
+    a.topl = 0; a.top = nullptr; a.surface = nullptr; a.status = status_dev; a.surface_in = surface;
+    const size_t sm = sm0 + 4 * per_peak + 16;
+    CK(ensure_smem(k_peak_search, (int)sm));
     k_peak_search<<<B, PEAK_NT, sm, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return 0;
@@ -793,7 +834,7 @@ extern "C" int admmnet_tc_gemm_probe(const float* A, const float* B, const float
         if (!make_tmap_2d_f32(&tmA, A, 128, K, (uint64_t)K * 4, 128, K) || !make_tmap_2d_f32(&tmB, B, N, K, (uint64_t)K * 4, N, K))
             return fail(ADMMNET_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
-    CK(cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(ensure_smem(k_tc_probe, (int)sm));
     k_tc_probe<<<1, 128, sm, (cudaStream_t)stream>>>(a, tmA, tmB);
     CK(cudaGetLastError());
     return 0;
@@ -888,7 +929,7 @@ extern "C" int admmnet_peak_head(const void* phi, int B, int n, int L, const flo
     HeadArgs2 a;
     a.phi = (const float2*)phi; a.P = head_params; a.tau = tau; a.f = f; a.conf = conf; a.B = B; a.n = n; a.L = L;
     const size_t sm = (size_t)(HS * 2 * n + 3 * HS * HD + HS * HEADS * n) * sizeof(float);
-    CK(cudaFuncSetAttribute(k_peak_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(ensure_smem(k_peak_head, (int)sm));
     prof::Scope pscope(prof::MISC, (cudaStream_t)stream);
     k_peak_head<<<(B + HS - 1) / HS, HD, sm, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());

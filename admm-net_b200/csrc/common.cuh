@@ -5,6 +5,23 @@
 
 #define ADMM_EPS 1e-8f
 
+// Bounds / invariant checks for debug builds (python admm-net_b200/build.py --debug  ->  -DADMMNET_DEBUG): the GPU
+// pool has compute-sanitizer closed, so index arithmetic of the shared-memory tilings is checked in-kernel instead.
+// A failing check prints file:line and traps (the launch then reports an error instead of corrupting memory).
+#ifdef ADMMNET_DEBUG
+#include <cstdio>
+#define ADMM_ASSERT(cond)                                                                              \
+    do {                                                                                               \
+        if (!(cond)) {                                                                                 \
+            printf("ADMM_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                 \
+            __trap();                                                                                  \
+        }                                                                                              \
+    } while (0)
+#else
+#define ADMM_ASSERT(cond) ((void)0)
+#endif
+
 namespace admmnet {
 
 // ---------------------------------------------------------------- packed parameter layout (floats)

@@ -30,6 +30,7 @@ struct PeakArgs {
     double* top;           // [B][topl][3]
     double* surface;       // optional [B][Gy][Gx]
     int* status;
+    const double* surface_in;  // optional [B][Gy][Gx]: debug tap, the local-maximum stage runs on THIS surface
 };
 
 #define TWO_PI_D 6.283185307179586   // == 2*np.pi in binary64
@@ -120,18 +121,18 @@ __global__ void __launch_bounds__(PEAK_NT) k_peak_search(PeakArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int sig = blockIdx.x;
 
-    for (int i = tid; i < n; i += PEAK_NT) {
+    for (int i = tid; i < n && !a.surface_in; i += PEAK_NT) {
         if (a.phi_is_c128) phis[i] = reinterpret_cast<const double2*>(a.phi)[(size_t)sig * n + i];
         else {
             const float2 v = reinterpret_cast<const float2*>(a.phi)[(size_t)sig * n + i];
             phis[i] = make_double2((double)v.x, (double)v.y);
         }
     }
-    for (int i = tid; i < Gy * yb; i += PEAK_NT) Sy[i] = steer(a.axis_y[i / yb], i % yb, yb);
-    for (int i = tid; i < Gx * xb; i += PEAK_NT) Dx[i] = steer(a.axis_x[i % Gx], i / Gx, xb);   // [xb][Gx]
+    for (int i = tid; i < Gy * yb && !a.surface_in; i += PEAK_NT) Sy[i] = steer(a.axis_y[i / yb], i % yb, yb);
+    for (int i = tid; i < Gx * xb && !a.surface_in; i += PEAK_NT) Dx[i] = steer(a.axis_x[i % Gx], i / Gx, xb);   // [xb][Gx]
     __syncthreads();
     // T[iy][q] = sum_p conj(phi[p][q]) * Sy[iy][p]
-    for (int i = tid; i < Gy * xb; i += PEAK_NT) {
+    for (int i = tid; i < Gy * xb && !a.surface_in; i += PEAK_NT) {
         const int iy = i / xb, q = i % xb;
         double2 acc = make_double2(0.0, 0.0);
         for (int p = 0; p < yb; ++p) {
@@ -145,13 +146,18 @@ __global__ void __launch_bounds__(PEAK_NT) k_peak_search(PeakArgs a) {
     double lmin = INFINITY, lmax = -INFINITY;
     for (int i = tid; i < N; i += PEAK_NT) {
         const int iy = i / Gx, ix = i % Gx;
-        double2 acc = make_double2(0.0, 0.0);
-        for (int q = 0; q < xb; ++q) {
-            const double2 t = T[iy * xb + q], dq = Dx[q * Gx + ix];
-            acc.x += t.x * dq.x + t.y * dq.y;
-            acc.y += t.y * dq.x - t.x * dq.y;
+        double z;
+        if (a.surface_in) {
+            z = a.surface_in[(size_t)sig * N + i];
+        } else {
+            double2 acc = make_double2(0.0, 0.0);
+            for (int q = 0; q < xb; ++q) {
+                const double2 t = T[iy * xb + q], dq = Dx[q * Gx + ix];
+                acc.x += t.x * dq.x + t.y * dq.y;
+                acc.y += t.y * dq.x - t.x * dq.y;
+            }
+            z = abs2_np(acc);
         }
-        const double z = abs2_np(acc);
         Z[i] = z;
         lmin = fmin(lmin, z);
         lmax = fmax(lmax, z);
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(PEAK_NT) k_peak_search(PeakArgs a) {
         const int pix = plist[k];
         out[3 * k] = a.axis_x[pix % Gx];
         out[3 * k + 1] = a.axis_y[pix / Gx];
-        out[3 * k + 2] = 0.0;
+        out[3 * k + 2] = a.surface_in ? Z[pix] : 0.0;
     }
     __syncthreads();
     for (int base = 0; base < Pst; base += PT) {

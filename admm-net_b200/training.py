@@ -29,7 +29,7 @@ def allreduce_gradients(model, group=None, weight=1.0):
         off += nel
 
 
-def train_step(model, criterion, optimizer, y, b, sigma, phi_true, max_norm=1.0, group=None):
+def train_step(model, criterion, optimizer, y, b, sigma, phi_true, max_norm=1.0, group=None, check_status=True):
     """optimizer.zero_grad -> forward -> loss -> backward -> all-reduce -> clip -> step  (trainPhi.py:165-178).
     A rank with an empty shard (y.shape[0] == 0: tail batch smaller than the world size) skips forward/backward but
     still joins the all-reduce with weight 0 and applies the same optimizer step, so the replicas stay in sync."""
@@ -46,16 +46,208 @@ def train_step(model, criterion, optimizer, y, b, sigma, phi_true, max_norm=1.0,
     allreduce_gradients(model, group, weight=nloc)
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
     optimizer.step()
+    if check_status and y.is_cuda:
+        from .autograd import eigh_status
+        if eigh_status(y.device):
+            raise RuntimeError("eigen-solver did not converge during the training step")
     return loss.detach(), parts
 
 
-def make_optimizer(model, lr=5e-3, weight_decay=1e-3):
-    """trainPhi.py:100-118: AdamW on the four layer lists at lr/2, cosine warm restarts (T_0=10, T_mult=2)."""
+def make_optimizer(model, lr=5e-3, weight_decay=1e-3, capturable=False, with_head=False):
+    """trainPhi.py:100-118: AdamW on the four layer lists at lr/2, cosine warm restarts (T_0=10, T_mult=2).
+    with_head=True adds train.py:104-121's second group (every other parameter at the full lr).
+    capturable=True keeps the optimizer state on the device so the step can live inside a CUDA graph."""
     admm_params = [p for name, p in model.named_parameters()
                    if any(prefix in name for prefix in ("phiLayers", "hLayers", "gLayers", "zLayers"))]
-    optimizer = torch.optim.AdamW([{"params": admm_params, "lr": lr * 0.5}], lr=lr, weight_decay=weight_decay)
+    groups = [{"params": admm_params, "lr": lr * 0.5}]
+    if with_head:
+        other = [p for p in model.parameters() if not any(p is q for q in admm_params)]
+        if other:
+            groups.append({"params": other, "lr": lr})
+    optimizer = torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, capturable=capturable)
     scheduler = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(optimizer, T_0=10, T_mult=2, eta_min=1e-6)
     return optimizer, scheduler
+
+
+class GraphedTrainStep:
+    """One training step (trainPhi.py:165-178: zero_grad, forward, loss, backward, gradient all-reduce, clip, AdamW)
+    captured ONCE in a CUDA graph and replayed: at batch 256 the step is ~2000 small launches and launch bound when
+    run eagerly.  Inputs are copied into static buffers; shapes are fixed (a ragged tail batch runs through the
+    eager `train_step`).  The optimizer must be capturable (make_optimizer(..., capturable=True)).  The three eager
+    warm-up steps PyTorch's capture needs are run on a snapshot of the model/optimizer state, which is restored
+    before the capture, so graph mode takes exactly the same parameter trajectory as eager mode."""
+
+    def __init__(self, model, criterion, optimizer, example, max_norm=1.0, group=None):
+        import copy
+        self.model, self.criterion, self.optimizer, self.max_norm, self.group = model, criterion, optimizer, max_norm, group
+        self.static = [t.clone() for t in example]
+        snap_m = copy.deepcopy(model.state_dict())
+        snap_o = copy.deepcopy(optimizer.state_dict())
+        model.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        model.load_state_dict(snap_m)
+        optimizer.load_state_dict(snap_o)
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _body(self):
+        y, b, sigma, phi_true = self.static
+        self.optimizer.zero_grad(set_to_none=True)
+        phi = self.model(y, b, sigma)
+        loss, _ = self.criterion(phi, phi_true)
+        loss.backward()
+        allreduce_gradients(self.model, self.group, weight=y.shape[0])
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_norm)
+        self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, y, b, sigma, phi_true):
+        for dst, src in zip(self.static, (y, b, sigma, phi_true)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
+def param_rmse(est, true, L_true):
+    """train.py:279-294 without the per-sample Python loop: for every sample with L > 0 true targets
+    sqrt(mean((est[:L] - true[:L])^2)); returns the vector of those values (train.py averages them with np.mean)."""
+    Lmax = est.shape[1]
+    L = L_true.reshape(-1, 1).to(est.device)
+    mask = (torch.arange(Lmax, device=est.device).unsqueeze(0) < L).to(est.dtype)
+    mse = (mask * (est - true) ** 2).sum(1) / L.clamp(min=1).reshape(-1).to(est.dtype)
+    return torch.sqrt(mse)[L.reshape(-1) > 0]
+
+
+def detection_counts(confidences, L_true, threshold=0.5):
+    """train.py:409-421: per sample detected = #(confidence > threshold); TP += min(L, detected) when both are
+    positive, FP += max(detected - L, 0), FN += max(L - detected, 0).  Returns (tp, fp, fn) as Python ints."""
+    L = L_true.reshape(-1).to(confidences.device).long()
+    det = (confidences > threshold).sum(1)
+    tp = torch.where((L > 0) & (det > 0), torch.minimum(L, det), torch.zeros_like(L)).sum()
+    fp = (det - L).clamp(min=0).sum()
+    fn = (L - det).clamp(min=0).sum()
+    return int(tp), int(fp), int(fn)
+
+
+def detection_scores(tp, fp, fn):
+    """train.py:437-443: precision, recall, F1 (0 when undefined)."""
+    precision = tp / (tp + fp) if (tp + fp) > 0 else 0
+    recall = tp / (tp + fn) if (tp + fn) > 0 else 0
+    f1 = 2 * precision * recall / (precision + recall) if (precision + recall) > 0 else 0
+    return precision, recall, f1
+
+
+def _admmnet_loss(model, criterion, batch, device):
+    y, b, tau, f, L, sigma = (t.to(device, non_blocking=True) for t in batch)
+    tau_est, f_est, conf, phi = model(y, b, sigma)
+    total, parts = criterion({"tau_est": tau_est, "f_est": f_est, "confidences": conf, "phi_final": phi},
+                             {"tau_true": tau, "f_true": f, "L_true": L, "y": y, "b": b})
+    return total, (tau_est, f_est, conf, tau, f, L)
+
+
+def evaluate_admmnet(model, criterion, split, batch_size=256, device="cuda", detection=False):
+    """Validation / test pass of train.py (217-294 and 372-434): mean batch loss, tau / f RMSE over the samples with
+    targets, and (test) the detection statistics.  `split` is a tuple of dataset.load_split."""
+    model.eval()
+    sel = (split[0], split[1], split[2], split[3], split[5], split[6])       # y, b, tau, f, L, sigma
+    tot, nb, te, fe = 0.0, 0, [], []
+    tp = fp = fn = 0
+    with torch.no_grad():
+        for lo in range(0, sel[0].shape[0], batch_size):
+            loss, (tau_est, f_est, conf, tau, f, L) = _admmnet_loss(model, criterion, tuple(t[lo:lo + batch_size] for t in sel), device)
+            tot += float(loss)
+            nb += 1
+            te.append(param_rmse(tau_est, tau, L))
+            fe.append(param_rmse(f_est, f, L))
+            if detection:
+                a, b_, c = detection_counts(conf, L)
+                tp, fp, fn = tp + a, fp + b_, fn + c
+    te, fe = torch.cat(te), torch.cat(fe)
+    out = {"loss": tot / max(nb, 1), "tau_rmse": float(te.mean()) if te.numel() else 0.0,
+           "f_rmse": float(fe.mean()) if fe.numel() else 0.0}
+    if detection:
+        p, r, f1 = detection_scores(tp, fp, fn)
+        out.update(precision=p, recall=r, f1_score=f1,
+                   detection_stats={"true_positive": tp, "false_positive": fp, "false_negative": fn})
+    return out
+
+
+def fit_admmnet(model, train, val, test, config, device="cuda", group=None, log=print):
+    """train.py:160-447 for the full ADMMNet (tau/f/confidence head, BasicANMLoss): epochs of train / validate with tau
+    and f RMSE / cosine-restart scheduler step / checkpoint on the best validation loss / early stopping with patience
+    10, then the test pass on the best checkpoint with precision, recall and F1 at confidence 0.5.  Data parallel like
+    `fit`: every global batch is split over the ranks, one flat gradient all-reduce per step.  Returns
+    (history, test_result); with config['log_dir'] both are also written as training_history.json / test_result.json."""
+    import json
+    import os
+
+    from .autograd import BasicANMLoss
+    from .dataset import load_checkpoint, save_checkpoint
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    criterion = BasicANMLoss()
+    optimizer, scheduler = make_optimizer(model, config.get("lr", 1e-3), config.get("weight_decay", 1e-3), with_head=True)
+    start_epoch, best_val, patience, bad = 0, float("inf"), config.get("patience", 10), 0
+    ck_path = os.path.join(config["checkpoint_dir"], "best_model.pth") if config.get("checkpoint_dir") else None
+    if ck_path and os.path.exists(ck_path):
+        start_epoch, best_val, _ = load_checkpoint(ck_path, model, optimizer, scheduler, map_location=device)
+    history = {"train_loss": [], "val_loss": [], "tau_rmse": [], "f_rmse": [], "lr": []}
+    sel = lambda t: (t[0], t[1], t[2], t[3], t[5], t[6])                      # y, b, tau, f, L, sigma
+    gen = torch.Generator().manual_seed(config.get("seed", 0))
+    bs = config.get("batch_size", 256)
+    for epoch in range(start_epoch, config.get("epochs", 100)):
+        model.train()
+        order = torch.randperm(train[0].shape[0], generator=gen)
+        tot, nb = 0.0, 0
+        for batch in _batches(sel(train), bs, order, rank, world):
+            optimizer.zero_grad()
+            nloc = batch[0].shape[0]
+            if nloc:
+                loss, _ = _admmnet_loss(model, criterion, batch, device)
+                loss.backward()
+                tot += float(loss)
+                nb += 1
+            allreduce_gradients(model, group, weight=nloc)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+            optimizer.step()
+        ev = evaluate_admmnet(model, criterion, val, bs, device)
+        history["train_loss"].append(tot / max(nb, 1))
+        history["val_loss"].append(ev["loss"])
+        history["tau_rmse"].append(ev["tau_rmse"])
+        history["f_rmse"].append(ev["f_rmse"])
+        history["lr"].append(optimizer.param_groups[0]["lr"])
+        log(f"epoch {epoch + 1}: train {history['train_loss'][-1]:.6f}  val {ev['loss']:.6f}  "
+            f"tau RMSE {ev['tau_rmse']:.6f}  f RMSE {ev['f_rmse']:.6f}  lr {history['lr'][-1]:.2e}")
+        scheduler.step()
+        if ev["loss"] < best_val:
+            best_val, bad = ev["loss"], 0
+            if ck_path and rank == 0:
+                save_checkpoint(ck_path, epoch, model, optimizer, scheduler, best_val, config, history)
+        else:
+            bad += 1
+        if config.get("log_dir") and rank == 0:
+            with open(os.path.join(config["log_dir"], "training_history.json"), "w") as fh:
+                json.dump({k: [float(x) for x in v] for k, v in history.items()}, fh, indent=2)
+        if bad >= patience:
+            break
+    if ck_path and os.path.exists(ck_path):
+        load_checkpoint(ck_path, model, map_location=device)
+    res = evaluate_admmnet(model, criterion, test, bs, device, detection=True)
+    test_result = {"test_loss": res["loss"], "tau_rmse": res["tau_rmse"], "f_rmse": res["f_rmse"],
+                   "precision": res["precision"], "recall": res["recall"], "f1_score": res["f1_score"],
+                   "detection_stats": res["detection_stats"]}
+    if config.get("log_dir") and rank == 0:
+        with open(os.path.join(config["log_dir"], "test_result.json"), "w") as fh:
+            json.dump(test_result, fh, indent=2)
+    return history, test_result
 
 
 def _batches(tensors, batch_size, order, rank, world):

@@ -150,7 +150,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def torch_cuda_baseline(dev, B=4096, reps=2):
+def torch_cuda_baseline(dev, B=512, reps=1):
     """BASELINE.md §3.4 "the GPU bar to beat": the reference's own op sequence (oracle port of
     PhiEstADMMNet.forward: torch.linalg.eigh -> cuSOLVER, bmm -> cuBLAS, ~150 torch ops per layer) with all
     tensors on the B200, no_grad.  /root/reference does not exist on the GPU box, so the op-for-op port is what
@@ -211,6 +211,96 @@ def parity_check(model, yd, bd, sd_, phi_dev, top_dev, means, n_fwd=64, n_peak=8
     return {"signals_checked": int(n_fwd), "phi_rel_max": float(rel.max()), "phi_rel_median": float(rel.median()),
             "peaks_checked": int(n_peak), "peaks_identical": bool(same), "tolerance": 1e-4,
             "how": "CPU oracle on a random subset of the timed batch with the device's per-layer batch means"}
+
+
+def run_train(args):
+    """BASELINE.json configs[4] (trainPhi.py recipe, SURVEY.md §8d cfg 5): PhiEstADMMNet K=10, PhiAlignmentLoss, AdamW
+    + gradient clipping, batch 256 per GPU, labels phi from the classical solver, one flat NCCL gradient all-reduce per
+    step.  The step (forward, backward, all-reduce, clip, optimizer) is captured in one CUDA graph and replayed; the
+    e2e figure adds the pinned-host -> device copy of every batch and the device -> host read of the loss."""
+    import admmnet_b200
+    import torch.distributed as dist
+    from admmnet_b200.autograd import PhiAlignmentLoss, eigh_status
+    from admmnet_b200.training import GraphedTrainStep, make_optimizer, train_step
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    Bt = args.train_batch
+    torch.manual_seed(0)
+    model = admmnet_b200.PhiEstADMMNet(M, N, 3, K_LAYERS).to(dev)
+    opt, _ = make_optimizer(model, 5e-3, 1e-3, capturable=True)
+    crit = PhiAlignmentLoss()
+    nbatch = 8
+    y, b, s = admmnet_b200.generate_signals(Bt * nbatch, M, N, 3, snr_w=20.0, snr_demod=7.0, seed=777 + rank, device=dev)
+    pt = admmnet_b200.admm_for_us_batched(y, b, 1.0, 5).to(torch.complex64)
+    host = [t.cpu().pin_memory() for t in (y, b, s, pt)]
+    ex = tuple(t[:Bt] for t in (y, b, s, pt))
+    mode = "cuda-graph"
+    try:
+        step = GraphedTrainStep(model, crit, opt, ex)
+    except Exception as e:                                   # e.g. NCCL capture refused: fall back to eager steps
+        mode = f"eager ({type(e).__name__})"
+        step = lambda *a: train_step(model, crit, opt, *a, check_status=False)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    dev_batches = [tuple(t[i * Bt:(i + 1) * Bt] for t in (y, b, s, pt)) for i in range(nbatch)]
+    losses = []
+
+    def step_dev(i):
+        losses.append(step(*dev_batches[i % nbatch]).clone())
+
+    def step_e2e(i):
+        bt = tuple(t[(i % nbatch) * Bt:(i % nbatch + 1) * Bt].to(dev, non_blocking=True) for t in host)
+        float(step(*bt))                                     # D2H read of the loss every step
+
+    for i in range(args.warmup):
+        step_dev(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    steps = max(args.steps, 20)
+    ms = timed(step_dev, steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, steps)
+    assert eigh_status(dev) == 0
+    first, last = float(losses[0]), float(losses[-1])
+    if rank == 0:
+        nparam = sum(p.numel() for p in model.parameters())
+        print(json.dumps({
+            "mode": "train", "metric": "training samples/s, trainPhi.py step (PhiEstADMMNet K=10, batch 256 per GPU)",
+            "value": world * Bt * steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE.json configs[4]: trainPhi.py step, K={K_LAYERS}, n={M}x{N}, batch {Bt} per GPU, "
+                                   "AdamW + clip 1.0, PhiAlignmentLoss, labels from the classical solver",
+                       "step_mode": mode, "allreduce_bytes_per_step": 4 * (nparam + 1) if world > 1 else 0},
+            "clocks": clocks, "loss_first": first, "loss_last": last,
+            "e2e": {"value": world * Bt * steps / (ms_e2e * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(sum(t[:Bt].nbytes for t in host)), "d2h_bytes_per_step": 4}}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def _time_ms(fn, reps):
@@ -319,11 +409,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward: the headline metric; train: the trainPhi.py step (BASELINE.json configs[4])")
+    ap.add_argument("--train-batch", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.impl == "torch-cuda":
         return run_torch_cuda(args)
+    if args.mode == "train":
+        return run_train(args)
 
     import admmnet_b200
     from admmnet_b200 import _capi, sharding

@@ -175,6 +175,12 @@ int admmnet_fp32_peak_launch(float* out, int grid, int iters, double* flops, voi
  * flags: 1 A from tensor memory, 2 negate A, 16 operands loaded by TMA, 32 3xTF32 split (arbitrary fp32 inputs,
  * fp32-class result), 64 accumulator at TMEM column 8.  No reference counterpart (unit test of the machinery).
  * ------------------------------------------------------------------------------------------- */
+/* Debug tap of the local-maximum stage (skimage.morphology.local_maxima(Z, connectivity=2), peakSearchUtils.py:118-119:
+ * 8-connected, plateau-aware, borders allowed, constant image has none) on a caller-supplied surface [B][Gy][Gx]:
+ * peaks[B][pmax][3] = (axis_x[ix], axis_y[iy], value) in row-major discovery order, count[B] the number found. */
+int peak_surface_maxima(const double* surface, int B, const double* axis_x, int Gx, const double* axis_y, int Gy,
+                        int pmax, double* peaks, int* count, int* status_dev, void* stream);
+
 /* shared-memory bytes of the tensor-core tail kernel (k_tail_tc) for matrix order d; -1: d outside its range
  * (33..104, the SIMT tail kernels serve), 0: switched off with ADMMNET_TAILTC=0 */
 int admmnet_tail_tc_smem_bytes(int d);

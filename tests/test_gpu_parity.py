@@ -471,6 +471,58 @@ def test_peak_plateau_and_degenerate_images(pkg):
     assert out.shape == (0, 3)                                  # n=1: |phi|^2 everywhere, one big plateau touching the border
 
 
+def _surface_maxima(pkg, img):
+    from admmnet_b200 import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda")
+    img = np.ascontiguousarray(img, dtype=np.float64)
+    B, Gy, Gx = img.shape
+    surf = torch.from_numpy(img).to(dev)
+    ax = torch.arange(Gx, dtype=torch.float64, device=dev)
+    ay = torch.arange(Gy, dtype=torch.float64, device=dev)
+    pmax = Gx * Gy
+    peaks = torch.zeros(B, pmax, 3, dtype=torch.float64, device=dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    _capi.check(L.peak_surface_maxima(surf.data_ptr(), B, ax.data_ptr(), Gx, ay.data_ptr(), Gy, pmax, peaks.data_ptr(),
+                                      cnt.data_ptr(), st.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    out = []
+    for i in range(B):
+        m = np.zeros((Gy, Gx), dtype=bool)
+        p = peaks[i, :int(cnt[i])].cpu().numpy()
+        m[p[:, 1].astype(int), p[:, 0].astype(int)] = True
+        out.append((m, p))
+    return out
+
+
+def test_local_maximum_stage_on_arbitrary_surfaces(pkg):
+    """the CUDA local-maximum stage fed with surfaces of our choosing — the reference's own
+    hand-checkable plateau KAT (peakSearchUtils.py:427-436), tie cases, border plateaus, and random images with many
+    exact ties against the oracle's restatement of skimage.morphology.local_maxima."""
+    from oracle import peak_oracle
+    kat = np.array([[1, 1, 1, 2, 3], [1, 5, 5, 4, 3], [2, 5, 5, 4, 2], [3, 4, 4, 3, 1]], dtype=np.float64)
+    want = np.zeros((4, 5), dtype=bool)
+    want[1:3, 1:3] = True                                      # the 2x2 plateau of fives, and nothing else
+    rng = np.random.default_rng(0)
+    cases = [kat,
+             np.array([[3, 3, 1, 0, 0], [3, 3, 1, 0, 2], [1, 1, 1, 0, 2], [0, 0, 0, 0, 2]], dtype=np.float64),   # border plateaus
+             np.array([[1, 2, 3, 4, 5], [1, 2, 3, 4, 5], [1, 2, 3, 4, 5], [1, 2, 3, 4, 5]], dtype=np.float64),   # ridge on the border
+             np.array([[2, 2, 2, 2, 2], [2, 1, 1, 1, 2], [2, 1, 3, 1, 2], [2, 2, 2, 2, 2]], dtype=np.float64),   # ring plateau + centre
+             np.array([[1, 1, 1, 1, 1], [1, 2, 2, 2, 1], [1, 2, 3, 2, 1], [1, 1, 1, 1, 1]], dtype=np.float64)]   # plateau below a peak
+    got = _surface_maxima(pkg, np.stack(cases))
+    assert np.array_equal(got[0][0], want)
+    for (m, _), img in zip(got, cases):
+        assert np.array_equal(m, peak_oracle.local_maxima(img, connectivity=2)), img
+    # row-major discovery order (np.where) and the values
+    m, p = got[0]
+    assert [tuple(r) for r in p[:, :2].astype(int)] == [(1, 1), (2, 1), (1, 2), (2, 2)] and np.all(p[:, 2] == 5.0)
+    # random images drawn from 4 levels: plateaus and ties everywhere
+    imgs = rng.integers(0, 4, size=(40, 13, 17)).astype(np.float64)
+    for (m, _), img in zip(_surface_maxima(pkg, imgs), imgs):
+        assert np.array_equal(m, peak_oracle.local_maxima(img, connectivity=2))
+
+
 def test_end_to_end_recovers_targets(pkg):
     """Physical sanity on the classical path (main.py:95-120): the three strongest peaks sit on the true (tau,f)."""
     from oracle import signals

@@ -420,3 +420,81 @@ def test_save_dataset_round_trip_and_no_cpu_generation(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(_capi.AdmmnetError):                 # the writer is a device path: no CPU fallback
             generate_dataset(str(tmp_path / "x"), total_samples=10)
+
+
+# ------------------------------------------------------------------ train.py loop and metrics
+def test_param_rmse_and_detection_match_the_reference_loops():
+    """train.py:279-294 (per-sample RMSE over the first L targets) and :409-443 (detection statistics, precision /
+    recall / F1), restated literally here as loops, against the vectorised forms."""
+    from admmnet_b200.training import detection_counts, detection_scores, param_rmse
+    g = torch.Generator().manual_seed(0)
+    B, Lmax = 57, 3
+    tau_est, tau_true = torch.rand(B, Lmax, generator=g), torch.rand(B, Lmax, generator=g)
+    conf = torch.rand(B, Lmax, generator=g)
+    L_true = torch.randint(0, Lmax + 1, (B,), generator=g)
+    want = []
+    for i in range(B):
+        L = L_true[i].item()
+        if L > 0:
+            want.append(torch.sqrt(torch.mean((tau_est[i, :L] - tau_true[i, :L]) ** 2)).item())
+    got = param_rmse(tau_est, tau_true, L_true)
+    assert got.shape[0] == len(want) and np.allclose(got.numpy(), np.array(want), rtol=1e-6, atol=1e-7)
+    tp = fp = fn = 0
+    for i in range(B):
+        L_i = L_true[i].item()
+        det = torch.sum(conf[i] > 0.5).item()
+        if L_i > 0 and det > 0:
+            tp += min(L_i, det)
+        if det > L_i:
+            fp += det - L_i
+        if L_i > det:
+            fn += L_i - det
+    assert detection_counts(conf, L_true) == (tp, fp, fn)
+    p, r, f1 = detection_scores(tp, fp, fn)
+    assert p == tp / (tp + fp) and r == tp / (tp + fn) and abs(f1 - 2 * p * r / (p + r)) < 1e-12
+    assert detection_scores(0, 0, 0) == (0, 0, 0)
+
+
+@pytest.mark.gpu
+def test_fit_admmnet_runs_the_train_py_loop_gpu(tmp_path):
+    """train.py:160-447 end to end on a small generated dataset: history keys, checkpoint, test metrics."""
+    import admmnet_b200
+    from admmnet_b200.dataset import generate_dataset, load_split
+    from admmnet_b200.training import fit_admmnet
+    data = str(tmp_path / "data")
+    generate_dataset(data, total_samples=240, seed=5)
+    train, val, test = (load_split(data, s) for s in ("train", "val", "test"))
+    torch.manual_seed(0)
+    model = admmnet_b200.ADMMNet(10, 10, 3, 3).cuda()
+    os.makedirs(tmp_path / "ck")
+    os.makedirs(tmp_path / "logs")
+    cfg = {"batch_size": 64, "epochs": 2, "lr": 1e-3, "weight_decay": 1e-3, "checkpoint_dir": str(tmp_path / "ck"),
+           "log_dir": str(tmp_path / "logs")}
+    history, result = fit_admmnet(model, train, val, test, cfg, log=lambda *a: None)
+    assert all(len(history[k]) == 2 for k in ("train_loss", "val_loss", "tau_rmse", "f_rmse", "lr"))
+    assert np.isfinite(history["train_loss"]).all() and history["tau_rmse"][-1] > 0
+    assert os.path.exists(tmp_path / "ck" / "best_model.pth")
+    assert set(result) == {"test_loss", "tau_rmse", "f_rmse", "precision", "recall", "f1_score", "detection_stats"}
+    assert 0 <= result["precision"] <= 1 and 0 <= result["recall"] <= 1
+    assert os.path.exists(tmp_path / "logs" / "training_history.json") and os.path.exists(tmp_path / "logs" / "test_result.json")
+
+
+@pytest.mark.gpu
+def test_cuda_graph_train_step_matches_eager_gpu():
+    """GraphedTrainStep replays the captured step: same losses and parameters as the eager train_step."""
+    from admmnet_b200.autograd import PhiAlignmentLoss, eigh_status
+    from admmnet_b200.training import GraphedTrainStep, make_optimizer, train_step
+    z, sd, _ = _load()
+    K = int(z["K"])
+    y, b, s, pt = (torch.from_numpy(z[k]).cuda() for k in ("y", "b", "sigma", "phi_true"))
+    crit = PhiAlignmentLoss()
+    m1, m2 = _model(sd, K, "cuda"), _model(sd, K, "cuda")
+    o1, _ = make_optimizer(m1, 5e-3, 1e-3, capturable=True)
+    o2, _ = make_optimizer(m2, 5e-3, 1e-3, capturable=True)
+    step = GraphedTrainStep(m2, crit, o2, (y, b, s, pt))
+    l1 = [float(train_step(m1, crit, o1, y, b, s, pt)[0]) for _ in range(4)]
+    l2 = [float(step(y, b, s, pt)) for _ in range(4)]
+    assert eigh_status(y.device) == 0
+    assert np.allclose(l1, l2, rtol=2e-3), (l1, l2)
+    for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert float((p1 - p2).abs().max()) <= 2e-3 * (float(p1.abs().max()) + 1e-3), n1
