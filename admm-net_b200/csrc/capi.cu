@@ -171,7 +171,17 @@ inline int next_stage_order(int d) {
         if (p.marks[i] <= TR_MAX && d > p.marks[i] + 8) return p.marks[i];
     return 0;     // finish in this stage
 }
-inline int stage1_steps(int d) { const int nx = next_stage_order(d); return nx ? d - nx : d - 1; }
+// register-resident tridiagonalisation (csrc/trd_reg.cuh): slots per thread, 0 = the shared-memory stages
+// (ADMMNET_TRD=0 selects them)
+inline int trd_ns(int d) {
+    static const bool on = !(getenv("ADMMNET_TRD") && atoi(getenv("ADMMNET_TRD")) == 0);
+    return !on ? 0 : (d <= 112 ? 7 : 8);
+}
+inline int stage1_steps(int d) {
+    if (trd_ns(d)) return d - 1;
+    const int nx = next_stage_order(d);
+    return nx ? d - nx : d - 1;
+}
 inline int default_rcap(int d) { return ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
 
 // n = signal length (for phi/h), d = matrix order.  Per-signal STATE arrays (Zp, GV, phi_cur, h_cur, r) cover
@@ -238,6 +248,7 @@ inline TearSpec dc_tears(int d, int B) {
 
 // later tridiagonalisation stages on the compacted trailing block (no-op when stage 1 did everything)
 int launch_head2(const Ws& w, int B, int d, cudaStream_t st, const int* skip = nullptr) {
+    if (trd_ns(d)) return 0;                 // the register-resident form finishes in k_head
     int dcur = next_stage_order(d);          // order handed over by k_head
     if (!dcur) return 0;
     const size_t tr_sz = (size_t)B * TR_MAX * TR_MAX;
@@ -514,10 +525,13 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     }
     h.skip = skip;
     const size_t sm = head_smem_bytes(d, h.ld);
-    CK(ensure_smem(k_head, (int)sm));
     {
+        const int ns = trd_ns(d);
+        CK(ensure_smem(ns == 7 ? k_head<7> : ns == 8 ? k_head<8> : k_head<0>, (int)sm));
         prof::Scope pscope(prof::HEAD, st);
-        k_head<<<Bc, 256, sm, st>>>(h);
+        if (ns == 7) k_head<7><<<Bc, 256, sm, st>>>(h);
+        else if (ns == 8) k_head<8><<<Bc, 256, sm, st>>>(h);
+        else k_head<0><<<Bc, 256, sm, st>>>(h);
     }
     CK(cudaGetLastError());
     if (int e = launch_head2(w, Bc, d, st, skip)) return e;
@@ -709,8 +723,14 @@ extern "C" int admmnet_eigh_batched(const void* A, int B, int d, float* evals, v
     cudaStream_t st = (cudaStream_t)stream;
     const int ld = d | 1;
     const size_t sm = head_smem_bytes(d, ld);
-    CK(ensure_smem(k_tridiag, (int)sm));
-    k_tridiag<<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT, w.Ttr, stage1_steps(d));
+    {
+        prof::Scope pscope(prof::HEAD, st);
+        const int ns = trd_ns(d);
+        CK(ensure_smem(ns == 7 ? k_tridiag<7> : ns == 8 ? k_tridiag<8> : k_tridiag<0>, (int)sm));
+        if (ns == 7) k_tridiag<7><<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT, w.Ttr, d - 1);
+        else if (ns == 8) k_tridiag<8><<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT, w.Ttr, d - 1);
+        else k_tridiag<0><<<B, 256, sm, st>>>((const float2*)A, B, d, ld, w.GV, w.tau, w.dT, w.eT, w.Ttr, stage1_steps(d));
+    }
     CK(cudaGetLastError());
     if (int e = launch_head2(w, B, d, st)) return e;
     if (int e = launch_eig_tail(w, B, d - 1, d, rcap, params, params ? 0 : -1, (float2*)evecs, nullptr, status_dev, st))

@@ -14,6 +14,7 @@
 //   k_mean   : batch mean of r (admm_net.py:459), deterministic.
 // The last layer only needs the phi-update (k_final_phi): its H/G/Z updates never reach the output.
 #include "common.cuh"
+#include "trd_reg.cuh"
 
 namespace admmnet {
 
@@ -283,6 +284,16 @@ __device__ void export_tridiag(const float2* __restrict__ A, int d, int ld, cons
     }
 }
 
+// d, e, tau of a complete reduction (the register-resident form stores its reflectors itself)
+__device__ void export_de(const float2* tau_s, const float* dd, const float* ee, float2* __restrict__ taug,
+                          float* __restrict__ dT, float* __restrict__ eT, int B, int sig, int d) {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        taug[i] = i < d - 1 ? tau_s[i] : make_float2(0.f, 0.f);
+        dT[(size_t)i * B + sig] = dd[i];
+        eT[(size_t)i * B + sig] = i < d - 1 ? ee[i] : 0.f;
+    }
+}
+
 // shared-memory carve-up shared by k_head and k_tridiag
 struct HeadSmem {
     float2* A;
@@ -299,8 +310,13 @@ struct HeadSmem {
     float* hid;     // [64]
     float* h;       // [n]
 };
+// the staging copy of A doubles as the scratch of the register-resident tridiagonalisation (trd_reg.cuh)
+__host__ __device__ inline size_t head_a_f2(int d, int ld) {
+    const size_t a = (size_t)d * ld;
+    return a > (size_t)TRD_SCRATCH_F2 ? a : (size_t)TRD_SCRATCH_F2;
+}
 __host__ __device__ inline size_t head_smem_bytes(int d, int ld) {
-    size_t f2 = (size_t)d * ld + 1 /*align*/ + 256 /*vw*/ + 128 /*vn*/ + 1024 /*part*/ + 4 + 128 /*tau*/ +
+    size_t f2 = head_a_f2(d, ld) + 1 /*align*/ + 256 /*vw*/ + 128 /*vn*/ + 1024 /*part*/ + 4 + 128 /*tau*/ +
                 4 * 128 /*phi,gcol,zeta,phip*/;
     size_t f1 = 96 + 128 + 128 /*dd,ee*/ + 128 /*hp*/ + 128 /*t*/ + 64 + 128 /*h*/;
     return f2 * sizeof(float2) + f1 * sizeof(float);
@@ -308,8 +324,8 @@ __host__ __device__ inline size_t head_smem_bytes(int d, int ld) {
 __device__ inline HeadSmem carve_head(unsigned char* base, int d, int ld) {
     HeadSmem s;
     float2* p2 = reinterpret_cast<float2*>(base);
-    s.A = p2; p2 += (size_t)d * ld;
-    p2 += ((size_t)d * ld) & 1;                          // float4 alignment of vw
+    s.A = p2; p2 += head_a_f2(d, ld);
+    p2 += head_a_f2(d, ld) & 1;                          // float4 alignment of vw
     s.S.vw = reinterpret_cast<float4*>(p2); p2 += 256;
     s.S.vn = p2; p2 += 128;
     s.S.part = p2; p2 += 1024;
@@ -351,7 +367,10 @@ struct HeadArgs {
     const int* skip;     // optional [B]: 1 = signal already handled by k_arrow (layer 0)
 };
 
-__global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
+// NS = 0: shared-memory tridiagonalisation, possibly continued by k_head2 stages (a.k1 < d-1);
+// NS = 7 / 8: register-resident form (d <= 112 / 128), always complete.
+template <int NS>
+__global__ void __launch_bounds__(256, NS == 8 ? 1 : 2) k_head(HeadArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, d = a.d, ld = a.ld;
     HeadSmem s = carve_head(smem_raw, d, ld);
@@ -476,6 +495,11 @@ __global__ void __launch_bounds__(256, 2) k_head(HeadArgs a) {
     if (tid == 0) s.A[n + (size_t)n * ld].x += P[P_C0];
     __syncthreads();
     // ---- eigh, stage 1
+    if (NS > 0) {
+        tridiag_reg<(NS > 0 ? NS : 7)>(s.A, d, ld, s.S.vw, s.S.vn, s.tau, s.dd, s.ee, GV);
+        export_de(s.tau, s.dd, s.ee, a.tau + (size_t)sig * d, a.dT, a.eT, a.B, sig, d);
+        return;
+    }
     tridiag_smem<256, 128>(s.A, d, ld, s.S, s.tau, s.dd, s.ee, a.k1);
     const bool full = a.k1 >= d - 1;
     export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, GV, a.tau + (size_t)sig * d, a.dT, a.eT, a.B, sig, 0, d,
@@ -540,7 +564,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 3) k_head2(Head2Args a) {
 
 // Debug/unit entry: tridiagonalise arbitrary Hermitian matrices given as full row-major [B][d][d]
 // (lower triangle is read).
-__global__ void __launch_bounds__(256, 2)
+template <int NS>
+__global__ void __launch_bounds__(256, NS == 8 ? 1 : 2)
 k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, float2* tau, float* dT, float* eT,
           float2* Ttr, int k1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -558,6 +583,11 @@ k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, flo
         }
     }
     __syncthreads();
+    if (NS > 0) {
+        tridiag_reg<(NS > 0 ? NS : 7)>(s.A, d, ld, s.S.vw, s.S.vn, s.tau, s.dd, s.ee, V + (size_t)sig * npk);
+        export_de(s.tau, s.dd, s.ee, tau + (size_t)sig * d, dT, eT, B, sig, d);
+        return;
+    }
     tridiag_smem<256, 128>(s.A, d, ld, s.S, s.tau, s.dd, s.ee, k1);
     const bool full = k1 >= d - 1;
     export_tridiag(s.A, d, ld, s.tau, s.dd, s.ee, V + (size_t)sig * npk, tau + (size_t)sig * d, dT, eT, B, sig, 0, d,

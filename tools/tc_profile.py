@@ -54,6 +54,9 @@ if v[12]:
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 16
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 101
-    for env in ({"ADMMNET_TAILTC": "0"}, {"ADMMNET_TAILTC": "1", "ADMMNET_TC_PROF": "1"}):
+    envs = ({"ADMMNET_TAILTC": "0"}, {"ADMMNET_TAILTC": "1", "ADMMNET_TC_PROF": "1"})
+    if len(sys.argv) > 3:                       # e.g.  ... 2368 101 ADMMNET_TRD=0 ADMMNET_TRD=1
+        envs = [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[3:]]
+    for env in envs:
         print(env, flush=True)
         subprocess.run([sys.executable, "-c", CODE % (ROOT, B, d)], env=dict(os.environ, **env), check=False)
