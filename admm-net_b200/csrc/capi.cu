@@ -17,6 +17,7 @@
 #include "head_kernels.cu"
 #include "tc_probe.cu"
 #include "tail_tc.cu"
+#include "big_kernels.cu"
 
 using namespace admmnet;
 
@@ -54,8 +55,8 @@ static cudaError_t ensure_smem(F* func, int bytes) {
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
 // Process-global (guarded by a mutex); off by default (then the only cost is one branch per launch).
 namespace prof {
-enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, ARROW, NKINDS };
-static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge", "k_arrow"};
+enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, ARROW, BIG, NKINDS };
+static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge", "k_arrow", "k_big_layer"};
 struct Rec { int kind; cudaEvent_t a, b; };
 static bool on = false;
 static std::mutex mu;               // launches may come from several host threads while profiling is on
@@ -130,6 +131,7 @@ struct Ws {
     double* rho;
     int *nrot, *status;
     int* handled;      // [chunk] per slot: 1 = layer-0 signal solved by k_arrow
+    float2* big;       // d > 128 only: Jacobi scratch [slot][big_grid][2 d^2] (csrc/big_kernels.cu)
     double* rsum;
     size_t bytes;
 };
@@ -171,10 +173,11 @@ inline int next_stage_order(int d) {
         if (p.marks[i] <= TR_MAX && d > p.marks[i] + 8) return p.marks[i];
     return 0;     // finish in this stage
 }
-// register-resident tridiagonalisation (csrc/trd_reg.cuh): slots per thread, 0 = the shared-memory stages
-// (ADMMNET_TRD=0 selects them)
+// register-resident tridiagonalisation (csrc/trd_reg.cuh): slots per thread, 0 = the shared-memory stages.
+// Opt-in (ADMMNET_TRD=1): parity-green, but measured slower on B200 (752 ms against 304 + 333 ms per 131072 x 8
+// signal-layers for the staged form: 4 block barriers per Householder step at 2 CTAs per SM).
 inline int trd_ns(int d) {
-    static const bool on = !(getenv("ADMMNET_TRD") && atoi(getenv("ADMMNET_TRD")) == 0);
+    static const bool on = getenv("ADMMNET_TRD") && atoi(getenv("ADMMNET_TRD")) != 0;
     return !on ? 0 : (d <= 112 ? 7 : 8);
 }
 inline int stage1_steps(int d) {
@@ -182,7 +185,9 @@ inline int stage1_steps(int d) {
     const int nx = next_stage_order(d);
     return nx ? d - nx : d - 1;
 }
-inline int default_rcap(int d) { return ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
+inline int default_rcap(int d) { return d > 128 ? 2048 : ((2 * d * d + 2048 + 1023) / 1024) * 1024; }
+// d > 128 runs the size-agnostic Jacobi layer kernel (csrc/big_kernels.cu): persistent CTAs, two per SM
+inline int big_grid(int C) { return C < 296 ? C : 296; }
 
 // n = signal length (for phi/h), d = matrix order.  Per-signal STATE arrays (Zp, GV, phi_cur, h_cur, r) cover
 // the whole batch B; the eigen-solver SCRATCH (Zr, rot, tau, lam, dT, eT, nrot) covers one chunk C <= B.
@@ -194,17 +199,20 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
     auto take = [&](size_t nbytes) { unsigned char* q = p + off; off += al(nbytes); return q; };
     w.Zp = (float2*)take(B * npk * sizeof(float2));
     w.GV = (float2*)take(B * npk * sizeof(float2));
-    // two scratch slots so that consecutive chunks can be in flight on different streams
+    // two scratch slots so that consecutive chunks can be in flight on different streams; the Householder/QL scratch
+    // exists for d <= 128 only, the Jacobi scratch for d > 128 only
+    const size_t S = d > 128 ? 0 : (size_t)NSLOT * C;
     const size_t zsz = (size_t)d * (4 * ((d + 3) / 4));          // Z^T per signal: d rows of pitch 4*ceil(d/4)
-    w.Zr = (float*)take((size_t)NSLOT * C * zsz * sizeof(float));
-    w.Zr2 = (float*)take((size_t)NSLOT * C * zsz * sizeof(float));
-    w.rho = (double*)take((size_t)NSLOT * C * DC_MAXTEAR * sizeof(double));
-    w.rot = (float2*)take((size_t)NSLOT * C * rcap * sizeof(float2));
-    w.tau = (float2*)take((size_t)NSLOT * C * d * sizeof(float2));
-    w.Ttr = (float2*)take((size_t)NSLOT * C * 2 * TR_MAX * TR_MAX * sizeof(float2));   // ping-pong pair per slot
-    w.lam = (float*)take((size_t)NSLOT * C * d * sizeof(float));
-    w.dT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
-    w.eT = (float*)take((size_t)NSLOT * C * d * sizeof(float));
+    w.Zr = (float*)take(S * zsz * sizeof(float));
+    w.Zr2 = (float*)take(S * zsz * sizeof(float));
+    w.rho = (double*)take(S * DC_MAXTEAR * sizeof(double));
+    w.rot = (float2*)take(S * rcap * sizeof(float2));
+    w.tau = (float2*)take(S * d * sizeof(float2));
+    w.Ttr = (float2*)take(S * 2 * TR_MAX * TR_MAX * sizeof(float2));   // ping-pong pair per slot
+    w.lam = (float*)take(S * d * sizeof(float));
+    w.dT = (float*)take(S * d * sizeof(float));
+    w.eT = (float*)take(S * d * sizeof(float));
+    w.big = (float2*)take(d > 128 ? (size_t)NSLOT * big_grid(C) * big_scratch_f2(d) * sizeof(float2) : 0);
     w.phi_cur = (float2*)take((size_t)B * n * sizeof(float2));
     w.h_cur = (float*)take((size_t)B * n * sizeof(float));
     w.r = (float*)take((size_t)B * sizeof(float));
@@ -220,7 +228,7 @@ Ws carve(void* base, int B, int C, int n, int d, int K, int rcap) {
 int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
     if (B <= 0 || K <= 0) return fail(ADMMNET_ERR_ARG, "B and K must be positive");
     if (chunk <= 0 || chunk > B) chunk = B;
-    if (n < 2 || n > 127) return fail(ADMMNET_ERR_ARG, "n = M*N must be in [2,127] (matrix order d = n+1 <= 128)");
+    if (n < 2 || n > BIG_NMAX) return fail(ADMMNET_ERR_ARG, "n = M*N must be in [2,256]");
     if (rcap == 0) rcap = default_rcap(n + 1);
     if (rcap < 2048 || rcap % ROT_CHUNK) return fail(ADMMNET_ERR_ARG, "rcap must be a multiple of 1024, >= 2048");
     return 0;
@@ -411,6 +419,7 @@ static Ws chunk_view(const Ws& w, int off, int n, int d, int slot = 0, int C = 0
     c.eT += (size_t)slot * C * d;
     c.nrot += (size_t)slot * C;
     c.handled += (size_t)slot * C;
+    if (d > 128) c.big += (size_t)slot * big_grid(C) * big_scratch_f2(d);
     c.Zp += (size_t)off * npk;
     c.GV += (size_t)off * npk;
     c.phi_cur += (size_t)off * n;
@@ -498,6 +507,19 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     if (!ws || ws_bytes < wf.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
     Ws w = chunk_view(wf, sig_off, n, d, slot, chunk, rcap);
     const int ps = param_stride(n);
+    if (d > 128) {
+        // size-agnostic layer (cfg 4: n = 144, 196, 256): one persistent kernel per chunk, csrc/big_kernels.cu
+        BigArgs g;
+        g.y = (const float2*)y + (size_t)sig_off * n; g.b = (const float2*)b + (size_t)sig_off * n; g.sigma = sigma + sig_off;
+        g.Zp = w.Zp; g.GV = w.GV; g.phi_cur = w.phi_cur; g.h_cur = w.h_cur; g.r = w.r;
+        g.mean_prev = k > 0 ? w.mean + (k - 1) : w.mean;
+        g.Pk = params + (size_t)k * ps; g.Pkm1 = k > 0 ? params + (size_t)(k - 1) * ps : params;
+        g.scratch = w.big; g.status = w.status; g.B = Bc; g.n = n; g.d = d; g.first = (k == 0);
+        prof::Scope pscope(prof::BIG, st);
+        k_big_layer<<<big_grid(Bc), BIG_NT, 0, st>>>(g);
+        CK(cudaGetLastError());
+        return 0;
+    }
     HeadArgs h;
     h.y = (const float2*)y + (size_t)sig_off * n; h.b = (const float2*)b + (size_t)sig_off * n; h.sigma = sigma + sig_off;
     h.Zp = w.Zp; h.GV = w.GV; h.phi_cur = w.phi_cur; h.h_cur = w.h_cur; h.r_prev = w.r;
@@ -705,7 +727,7 @@ extern "C" int admmnet_arrow_eigh(const float* h, const void* phi, const float* 
 // ------------------------------------------------------------------------------------ eigh taps
 extern "C" int admmnet_eigh_workspace_bytes(int B, int d, int rcap, size_t* bytes) {
     if (!bytes) return fail(ADMMNET_ERR_ARG, "bytes is NULL");
-    if (B <= 0 || d < 3 || d > 128) return fail(ADMMNET_ERR_ARG, "need B > 0 and 3 <= d <= 128");
+    if (B <= 0 || d < 3 || d > BIG_NMAX + 1) return fail(ADMMNET_ERR_ARG, "need B > 0 and 3 <= d <= 257");
     if (rcap == 0) rcap = default_rcap(d);
     *bytes = carve(nullptr, B, B, d - 1, d, 1, rcap).bytes;
     return 0;
@@ -714,13 +736,20 @@ extern "C" int admmnet_eigh_workspace_bytes(int B, int d, int rcap, size_t* byte
 extern "C" int admmnet_eigh_batched(const void* A, int B, int d, float* evals, void* evecs, void* fn_out,
                                     const float* params, void* ws, size_t ws_bytes, int rcap, void* stream,
                                     int* status_dev) {
-    if (B <= 0 || d < 3 || d > 128) return fail(ADMMNET_ERR_ARG, "need B > 0 and 3 <= d <= 128");
+    if (B <= 0 || d < 3 || d > BIG_NMAX + 1) return fail(ADMMNET_ERR_ARG, "need B > 0 and 3 <= d <= 257");
     if (!A || !status_dev) return fail(ADMMNET_ERR_ARG, "null pointer");
     if (rcap == 0) rcap = default_rcap(d);
     if (rcap < 2048 || rcap % ROT_CHUNK) return fail(ADMMNET_ERR_ARG, "rcap must be a multiple of 1024, >= 2048");
     Ws w = carve(ws, B, B, d - 1, d, 1, rcap);
     if (!ws || ws_bytes < w.bytes) return fail(ADMMNET_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    if (d > 128) {       // Jacobi form (csrc/big_kernels.cu); eigenvalues come out unsorted
+        prof::Scope pscope(prof::BIG, st);
+        k_big_eigh<<<big_grid(B), BIG_NT, 0, st>>>((const float2*)A, B, d, evals, (float2*)evecs, (float2*)fn_out, params,
+                                                    w.big, status_dev);
+        CK(cudaGetLastError());
+        return 0;
+    }
     const int ld = d | 1;
     const size_t sm = head_smem_bytes(d, ld);
     {

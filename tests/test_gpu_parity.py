@@ -70,8 +70,32 @@ def test_eigh_random_hermitian(pkg, d):
     assert (ev.sort(dim=1)[0] - w).abs().amax() < 1e-5 * scale
 
 
+@pytest.mark.parametrize("d", [129, 145, 197, 257])
+def test_eigh_jacobi_large_orders(pkg, d):
+    """Matrix orders above 128 (cfg 4: n = 144, 196, 256) run the cyclic two-sided Jacobi kernel (csrc/big_kernels.cu):
+    eigenpairs against torch fp64, and f(A) through the eigenvalue map against the oracle's formula."""
+    from oracle import net_oracle
+    torch.manual_seed(d)
+    X = torch.randn(3, d, d, dtype=torch.complex64) * (3.0 / d ** 0.5)
+    A = 0.5 * (X + X.transpose(1, 2).conj())
+    A[2] = torch.diag(torch.linspace(-3, 5, d)).to(torch.complex64)          # already diagonal: zero rotations
+    net = pkg.PhiEstADMMNet(10, 10, 3, 2)
+    from admmnet_b200.params import pack_state_dict
+    P = pack_state_dict(net.state_dict(), 100, 2).cuda()
+    ev, U, G = _eigh(pkg, A, params=P[0], fn=True)
+    scale = torch.linalg.matrix_norm(A, ord=2).max().item()
+    assert (A @ U - U * ev.unsqueeze(1).to(torch.complex64)).abs().amax() < 2e-5 * scale
+    assert (U.transpose(1, 2).conj() @ U - torch.eye(d)).abs().amax() < 2e-5
+    w, Q = torch.linalg.eigh(A.to(torch.complex128))
+    assert (ev.sort(dim=1)[0] - w.float()).abs().amax() < 1e-5 * scale
+    lp = net_oracle.eig_map(w.float(), net_oracle.layer_params(net.state_dict(), 0)["g"]).to(torch.complex128)
+    ref = (Q * lp.unsqueeze(1)) @ Q.transpose(1, 2).conj()
+    assert (_unpack(G, d).to(torch.complex128) - ref).abs().amax() < 3e-5 * max(1.0, ref.abs().amax().item())
+
+
 def test_eigh_structured_cases(pkg):
     d = 101
+    torch.manual_seed(11)
     eye = torch.eye(d, dtype=torch.complex64)
     diag = torch.diag(torch.linspace(-3, 5, d)).to(torch.complex64)
     arrow = torch.diag(torch.full((d,), 0.01)).to(torch.complex64)          # layer-0 matrix: arrowhead
@@ -83,7 +107,7 @@ def test_eigh_structured_cases(pkg):
     A = torch.stack([eye, diag, arrow, rank1, torch.zeros(d, d, dtype=torch.complex64)])
     ev, U, _ = _eigh(pkg, A)
     assert (A @ U - U * ev.unsqueeze(1).to(torch.complex64)).abs().amax() < 2e-4
-    assert (U.transpose(1, 2).conj() @ U - torch.eye(d)).abs().amax() < 1e-5
+    assert (U.transpose(1, 2).conj() @ U - torch.eye(d)).abs().amax() < 2e-5      # fp32: a few d*eps (d*eps = 6e-6)
     w = torch.linalg.eigvalsh(A.to(torch.complex128)).float()
     assert (ev.sort(dim=1)[0] - w).abs().amax() < 2e-5 * 101
 
@@ -347,7 +371,9 @@ def test_forward_is_reentrant_across_host_threads_and_streams(pkg):
 def test_forward_other_shapes_and_edges(pkg):
     from oracle import net_oracle, signals
     torch.manual_seed(5)
-    for (M, N, K, B) in [(8, 8, 3, 5), (4, 6, 4, 3), (10, 10, 1, 4), (10, 10, 2, 1), (11, 11, 3, 2)]:
+    # (12,12), (14,14), (16,16): BASELINE.json configs[3]'s n = 144, 196, 256 (matrix order > 128: the Jacobi layer kernel)
+    for (M, N, K, B) in [(8, 8, 3, 5), (4, 6, 4, 3), (10, 10, 1, 4), (10, 10, 2, 1), (11, 11, 3, 2), (12, 12, 4, 3),
+                         (14, 14, 3, 2), (16, 16, 3, 2), (12, 13, 10, 2)]:
         net = pkg.PhiEstADMMNet(M, N, 3, K).eval()
         y, b, s, _ = signals.generate(B, Nb=M, Nd=N, seed=M * 100 + N)
         yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
@@ -359,8 +385,8 @@ def test_forward_other_shapes_and_edges(pkg):
     with pytest.raises(ValueError):
         net(torch.zeros(2, 99, dtype=torch.complex64), torch.zeros(2, 99, dtype=torch.complex64), torch.ones(2))
     with pytest.raises(Exception):
-        pkg.PhiEstADMMNet(12, 12, 3, 2)(torch.ones(1, 144, dtype=torch.complex64),
-                                       torch.ones(1, 144, dtype=torch.complex64), torch.ones(1))   # n > 127
+        pkg.PhiEstADMMNet(17, 17, 3, 2)(torch.ones(1, 289, dtype=torch.complex64),
+                                       torch.ones(1, 289, dtype=torch.complex64), torch.ones(1))   # n > 256
 
 
 def test_linearity_free_property_large_batch(pkg):
@@ -602,13 +628,13 @@ def test_admmnet_full_module_matches_reference_golden(pkg):
     np.testing.assert_allclose(t3.cpu().numpy(), z["tau"][:5], atol=2e-6, rtol=1e-5)
 
 
-@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILTC", "ADMMNET_LANES"])
+@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILTC", "ADMMNET_LANES", "ADMMNET_TRD=1"])
 def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
     """Every fast path has a plain sibling behind an environment switch (read once per process, hence the
     subprocess): ADMMNET_ARROW=0 dense eigen-solver at layer 0 instead of the arrowhead shortcut, ADMMNET_ROTF=0
     one sweep at a time in the rotation kernel, ADMMNET_TAILTC=0 the SIMT (FFMA2) back-transformation and rebuild
-    instead of the tcgen05 kernel,
-    ADMMNET_LANES=0 single stream.  Same inputs, same answer."""
+    instead of the tcgen05 kernel, ADMMNET_LANES=0 single stream, ADMMNET_TRD=1 the register-resident
+    tridiagonalisation (opt-in) instead of the staged shared-memory one.  Same inputs, same answer."""
     import subprocess
     import sys
     z, sd = load_net_case("pert_k10")
@@ -630,7 +656,8 @@ def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
         "with torch.no_grad():\n"
         f"    np.save({out!r}, net(y.repeat(300, 1), b.repeat(300, 1), s.repeat(300)).numpy())\n")
     env = dict(os.environ)
-    env[switch] = "0"
+    name, _, val = switch.partition("=")
+    env[name] = val or "0"
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
     phi_alt = np.load(out)
     assert rel_err(phi, phi_alt).max() < 3e-5
