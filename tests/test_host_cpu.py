@@ -38,7 +38,8 @@ def test_argument_errors_are_reported_not_crashed(built):
     nb = C.c_size_t()
     assert L.admmnet_forward_workspace_bytes(0, 0, 100, 10, 0, C.byref(nb)) < 0
     assert b"positive" in L.admmnet_last_error()
-    assert L.admmnet_forward_workspace_bytes(4, 0, 200, 10, 0, C.byref(nb)) < 0       # n > 127
+    assert L.admmnet_forward_workspace_bytes(4, 0, 300, 10, 0, C.byref(nb)) < 0       # n > 256
+    assert L.admmnet_forward_workspace_bytes(4, 0, 256, 10, 0, C.byref(nb)) == 0 and nb.value > 0   # Jacobi path sizes
     assert L.admmnet_forward_workspace_bytes(4, 0, 100, 10, 1000, C.byref(nb)) < 0    # rcap not a multiple of 1024
     assert L.admmnet_forward_workspace_bytes(1024, 256, 100, 10, 0, C.byref(nb)) == 0 and nb.value > 0
     small = nb.value
