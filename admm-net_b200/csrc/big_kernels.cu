@@ -66,6 +66,7 @@ __device__ void big_jacobi(float2* __restrict__ A, float2* __restrict__ V, int d
     if (!(fro < INFINITY)) { if (tid == 0) atomicOr(status, 4); return; }    // non-finite input
     const float stop = 4e-14f * fro;                   // (2e-7)^2 ||A||_F^2
     const float skip = 1e-18f * fro;                   // rotations below this are exact no-ops in fp32
+    bool converged = false;
     for (int sweep = 0; sweep < BIG_MAX_SWEEPS; ++sweep) {
         float off_acc = 0.f;                           // sum of |a_pq|^2 met by this thread's warp (lane 0 keeps it)
         for (int r = 0; r < dd - 1; ++r) {
@@ -86,7 +87,7 @@ __device__ void big_jacobi(float2* __restrict__ A, float2* __restrict__ V, int d
                         const float ab = sqrtf(b2);
                         const float tau = (aqq - app) / (2.f * ab);
                         const float tt = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-                        const float c = rsqrtf(1.f + tt * tt);
+                        const float c = 1.f / sqrtf(1.f + tt * tt);    // IEEE sqrt and division: c^2 + s^2 = 1 without the bias of rsqrtf
                         rt = make_float4(c, tt * c, apq.x / ab, apq.y / ab);
                         act = true;
                     }
@@ -136,9 +137,19 @@ __device__ void big_jacobi(float2* __restrict__ A, float2* __restrict__ V, int d
         float tot = 0.f;
         for (int w = 0; w < nw; ++w) tot += s.offsq[w];
         __syncthreads();
-        if (2.f * tot <= stop) return;
+        if (2.f * tot <= stop) { converged = true; break; }
     }
-    if (tid == 0) atomicOr(status, 2);                 // not converged within BIG_MAX_SWEEPS sweeps
+    if (!converged && tid == 0) atomicOr(status, 2);   // not converged within BIG_MAX_SWEEPS sweeps
+    // the columns of V went through ~d rotations per sweep: renormalise them (removes the accumulated norm drift)
+    for (int k = wid; k < d; k += nw) {
+        float2* Vk = V + (size_t)k * d;
+        float n2 = 0.f;
+        for (int row = lane; row < d; row += 32) { const float2 v = Vk[row]; n2 = fmaf(v.x, v.x, fmaf(v.y, v.y, n2)); }
+        n2 = warp_sum(n2);
+        const float inv = 1.f / sqrtf(n2);
+        for (int row = lane; row < d; row += 32) { const float2 v = Vk[row]; Vk[row] = make_float2(v.x * inv, v.y * inv); }
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(BIG_NT, 2) k_big_layer(BigArgs a) {
