@@ -39,6 +39,7 @@ _PROTOS = {
     "admmnet_profile_end": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "admmnet_tail_tc_smem_bytes": (_i, [_i]),
     "admmnet_tail_tc_profile_read": (_i, [_vp]),
+    "admmnet_dc_profile_read": (_i, [_vp]),
     "admmnet_tc_gemm_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "admmnet_fp32_peak_launch": (_i, [_vp, _i, _i, C.POINTER(_d), _vp]),
 }

@@ -8,21 +8,48 @@ The layer modules only HOLD parameters; the arithmetic of `PhiEstADMMNet.forward
 kernels behind include/admmnet_b200.h (no PyTorch/CPU fallback).
 
 Differences from the reference, all documented in DESIGN.md:
-  * eval-mode forward is an inference fast path (no autograd graph); in train() mode with grad enabled the forward
-    is the differentiable graph of autograd.py (CUDA eigen-solver + torch element-wise ops);
+  * in train() mode with grad enabled the forward is the differentiable graph of autograd.py (CUDA eigen-solver +
+    torch element-wise ops).  In eval() mode the values come from the fused inference kernels; with grad enabled the
+    result still carries a grad_fn (as the reference's does, test/test_time_net.py:94-100): its backward rebuilds the
+    differentiable graph on demand (_FusedForward), so `.backward()` works and costs nothing until it is called;
   * `norm_scope` / `chunk` attributes control how the ZLayer batch mean (admm_net.py:459) is scoped:
       'batch' (default) = the whole batch of the call, exactly like the reference;
       'chunk'           = independent chunks of `chunk` signals (throughput mode, no coupling);
   * `ADMMNet`'s learned PeakSearchLayer head (admm_net.py:494-630) runs with eval-mode semantics.
 """
 import ctypes as C
-import warnings
-
 import torch
 import torch.nn as nn
 
 from . import _capi
 from .params import pack_state_dict, param_stride
+
+
+class _FusedForward(torch.autograd.Function):
+    """Fast-path values with the reference's autograd contract: forward runs the fused inference kernels
+    (PhiEstADMMNet.forward_device); backward re-runs the layers as the differentiable graph of autograd.forward_train
+    on the saved inputs and back-propagates through it (recompute on demand, like activation checkpointing).  The
+    gradients are therefore exactly those of the train()-mode graph."""
+
+    @staticmethod
+    def forward(ctx, model, y, b, sigma, *params):
+        ctx.model = model
+        ctx.save_for_backward(y, b, sigma)
+        return model.forward_device(y, b, sigma)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .autograd import forward_train
+        model = ctx.model
+        ins = [t.detach().requires_grad_(ctx.needs_input_grad[1 + i]) for i, t in enumerate(ctx.saved_tensors)]
+        params = list(model.parameters())
+        wanted = [t for t in ins if t.requires_grad] + [p for p in params if p.requires_grad]
+        with torch.enable_grad():
+            out = forward_train(model, *ins)
+            got = iter(torch.autograd.grad(out, wanted, g, allow_unused=True))
+        g_ins = [next(got) if t.requires_grad else None for t in ins]
+        g_par = [next(got) if p.requires_grad else None for p in params]
+        return (None, *g_ins, *g_par)
 
 
 class PhiLayer(nn.Module):
@@ -122,7 +149,6 @@ class PhiEstADMMNet(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = None
-        self._warned = False
 
     # ------------------------------------------------------------------ parameters
     def packed_params(self, device):
@@ -149,7 +175,8 @@ class PhiEstADMMNet(nn.Module):
             raise ValueError("sigma must hold one value per signal ([B] or [B,1])")
         _capi.require_cuda()
         dev = y.device if y.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        to = lambda t, dt: t.detach().to(device=dev, dtype=dt, non_blocking=True).contiguous()
+        keep = torch.is_grad_enabled()      # inputs that require grad stay attached (the reference differentiates through them)
+        to = lambda t, dt: (t if keep and t.requires_grad else t.detach()).to(device=dev, dtype=dt, non_blocking=True).contiguous()
         return to(y, torch.complex64), to(b, torch.complex64), to(sigma.reshape(-1), torch.float32), dev
 
     def forward_device(self, y, b, sigma, out=None):
@@ -198,7 +225,8 @@ class PhiEstADMMNet(nn.Module):
         return st.value
 
     def forward(self, y, b, sigma):
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                                  or any(t.requires_grad for t in (y, b, sigma)))
         if needs_grad and self.training:
             # training: differentiable graph around the CUDA eigen-solver (autograd.py)
             from .autograd import forward_train
@@ -206,14 +234,16 @@ class PhiEstADMMNet(nn.Module):
             yd, bd, sd, _ = self._prep(y, b, sigma)
             out = forward_train(self, yd, bd, sd)
             return out if src_dev.type == "cuda" else out.to(src_dev)
-        if needs_grad and not self._warned:
-            warnings.warn("admmnet_b200: eval-mode forward is the inference fast path; the result is detached from "
-                          "autograd (call model.train() for the differentiable path)")
-            self._warned = True
         src_dev = y.device
         yd, bd, sd, _ = self._prep(y, b, sigma)
-        out = self.forward_device(yd, bd, sd)
+        out = self._forward_values(yd, bd, sd, needs_grad)
         return out if src_dev.type == "cuda" else out.to(src_dev)
+
+    def _forward_values(self, yd, bd, sd, needs_grad):
+        """Fused kernels; with grad enabled the result carries the lazily rebuilt graph (_FusedForward)."""
+        if needs_grad and self.norm_scope == "batch":
+            return _FusedForward.apply(self, yd, bd, sd, *self.parameters())
+        return self.forward_device(yd, bd, sd)
 
 
 class PeakSearchLayer(nn.Module):
@@ -300,17 +330,20 @@ class ADMMNet(PhiEstADMMNet):
         return tau, f, conf, phi
 
     def forward(self, y, b, sigma):
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                                  or any(t.requires_grad for t in (y, b, sigma)))
         src_dev = y.device
         yd, bd, sd, _ = self._prep(y, b, sigma)
         if needs_grad and self.training:
             outs = self.forward_differentiable(yd, bd, sd)
             return outs if src_dev.type == "cuda" else tuple(t.to(src_dev) for t in outs)
-        if needs_grad and not self._warned:
-            warnings.warn("admmnet_b200: eval-mode forward is the inference fast path; the result is detached from "
-                          "autograd (call model.train() for the differentiable path)")
-            self._warned = True
-        phi = self.forward_device(yd, bd, sd)
-        tau, f, conf = self.head_device(phi)
+        if needs_grad:
+            # eval mode with grad enabled: fused unrolled layers with the lazily rebuilt graph, head as torch modules
+            # (eval semantics: attention dropout off) so that the outputs are differentiable like the reference's
+            phi = self._forward_values(yd, bd, sd, True)
+            tau, f, conf = self.peakSearchLayer(phi, bd)
+        else:
+            phi = self.forward_device(yd, bd, sd)
+            tau, f, conf = self.head_device(phi)
         outs = (tau, f, conf, phi)
         return outs if src_dev.type == "cuda" else tuple(t.to(src_dev) for t in outs)

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libadmmnet_b200.so")
-SRC = [os.path.join(HERE, "csrc", f) for f in ("capi.cu", "net_kernels.cu", "arrow_kernels.cu", "classic_kernels.cu", "peak_kernels.cu", "gen_kernels.cu", "head_kernels.cu", "tc_probe.cu", "tc.cuh", "tail_tc.cu", "big_kernels.cu", "trd_reg.cuh",
+SRC = [os.path.join(HERE, "csrc", f) for f in ("capi.cu", "net_kernels.cu", "arrow_kernels.cu", "classic_kernels.cu", "peak_kernels.cu", "gen_kernels.cu", "head_kernels.cu", "tc_probe.cu", "tc.cuh", "tail_tc.cu", "big_kernels.cu", "dc_kernels.cu", "trd_reg.cuh",
                                                 "common.cuh")]
 HDR = os.path.join(os.path.dirname(HERE), "include", "admmnet_b200.h")
 

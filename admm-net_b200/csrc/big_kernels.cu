@@ -5,8 +5,8 @@
 // Same layer mathematics as k_head + k_tail (dual update of the previous layer, admm_net.py:388-412; phi-update 79-105;
 // H-update 134-194; block matrix 262-290; eigh 292-308; eigenvalue map 310-334; rebuild 336-354; residual norm 454),
 // same per-signal state (packed Z, packed G, phi, h, r).  The eigen-decomposition is a cyclic two-sided Jacobi method on
-// the full Hermitian matrix, which lives with its eigenvector matrix in a per-CTA global-memory scratch (2 d^2 complex,
-// L2 resident: 1 MB at d = 257):  rounds of floor((d+1)/2) disjoint plane rotations (round-robin tournament), each round
+// the full Hermitian matrix, which lives with its eigenvector matrix (and an untouched copy for the final Rayleigh
+// quotients) in a per-CTA global-memory scratch (3 d^2 complex, L2 resident: 1.6 MB at d = 257):  rounds of floor((d+1)/2) disjoint plane rotations (round-robin tournament), each round
 //   (1) rotation parameters from (a_pp, a_qq, a_pq) -> shared memory;  columns p, q of A and of V rotated  (A <- A J)
 //   (2) rows p, q of A rotated (A <- J^H A), a_pq := 0
 // until a sweep meets ||off(A)||_F <= 2e-7 ||A||_F (quadratic convergence; 6-9 sweeps in fp32).  Jacobi needs no
@@ -33,12 +33,12 @@ struct BigArgs {
     const float* mean_prev;
     const float* Pk;
     const float* Pkm1;
-    float2* scratch;     // [grid][2][d*d]
+    float2* scratch;     // [grid][3][d*d]: A (rotated in place), V, and the untouched copy A0 for the Rayleigh quotients
     int* status;
     int B, n, d, first;
 };
 
-__host__ __device__ inline size_t big_scratch_f2(int d) { return (size_t)2 * d * d; }
+__host__ __device__ inline size_t big_scratch_f2(int d) { return (size_t)3 * d * d; }
 
 struct BigSmem {
     float2 phi[BIG_NMAX], gcol[BIG_NMAX], zeta[BIG_NMAX], phip[BIG_NMAX];
@@ -51,19 +51,28 @@ struct BigSmem {
 };
 
 // Cyclic two-sided Jacobi on the Hermitian matrix A (column-major, leading dimension d, both triangles valid), V = I on
-// entry is accumulated.  On exit diag(A) holds the eigenvalues and the columns of V the eigenvectors.  All BIG_NT threads.
-__device__ void big_jacobi(float2* __restrict__ A, float2* __restrict__ V, int d, BigSmem& s, int* status) {
+// entry is accumulated.  On exit the columns of V hold the eigenvectors and s.lamp[k] the eigenvalue of column k, taken
+// as the Rayleigh quotient v_k^H A0 v_k against the copy A0 of the input made here: the diagonal of the rotated A carries
+// the rounding of ~d rotations per sweep (measured 2e-5 relative at d = 129..257), the quotient only that of one dot
+// product (its error is quadratic in the eigenvector error).  All BIG_NT threads.
+__device__ void big_jacobi(float2* __restrict__ A, float2* __restrict__ V, float2* __restrict__ A0, int d, BigSmem& s,
+                           int* status) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = BIG_NT / 32;
     const int dd = (d + 1) & ~1, npair = dd / 2;
     // ||A||_F^2
     float fro;
     {
         float v[1] = {0.f};
-        for (int idx = tid; idx < d * d; idx += BIG_NT) { const float2 x = A[idx]; v[0] += x.x * x.x + x.y * x.y; }
+        for (int idx = tid; idx < d * d; idx += BIG_NT) { const float2 x = A[idx]; A0[idx] = x; v[0] += x.x * x.x + x.y * x.y; }
         block_sum<1>(v, s.red);
         fro = v[0];
     }
-    if (!(fro < INFINITY)) { if (tid == 0) atomicOr(status, 4); return; }    // non-finite input
+    if (!(fro < INFINITY)) {                             // non-finite input
+        if (tid == 0) atomicOr(status, 4);
+        for (int i = tid; i < d; i += BIG_NT) s.lamp[i] = A[i + (size_t)i * d].x;
+        __syncthreads();
+        return;
+    }
     const float stop = 4e-14f * fro;                   // (2e-7)^2 ||A||_F^2
     const float skip = 1e-18f * fro;                   // rotations below this are exact no-ops in fp32
     bool converged = false;
@@ -148,6 +157,21 @@ __device__ void big_jacobi(float2* __restrict__ A, float2* __restrict__ V, int d
         n2 = warp_sum(n2);
         const float inv = 1.f / sqrtf(n2);
         for (int row = lane; row < d; row += 32) { const float2 v = Vk[row]; Vk[row] = make_float2(v.x * inv, v.y * inv); }
+        __syncwarp();
+        // Rayleigh quotient: lane owns rows lane, lane+32, ... of A0 v_k (A0 column-major: coalesced along rows)
+        float rq = 0.f;
+        for (int row = lane; row < d; row += 32) {
+            float ax = 0.f, ay = 0.f;
+            for (int j = 0; j < d; ++j) {
+                const float2 m = A0[row + (size_t)j * d], v = Vk[j];
+                ax = fmaf(m.x, v.x, fmaf(-m.y, v.y, ax));
+                ay = fmaf(m.x, v.y, fmaf(m.y, v.x, ay));
+            }
+            const float2 v = Vk[row];
+            rq = fmaf(v.x, ax, fmaf(v.y, ay, rq));
+        }
+        rq = warp_sum(rq);
+        if (lane == 0) s.lamp[k] = rq;
     }
     __syncthreads();
 }
@@ -158,6 +182,7 @@ __global__ void __launch_bounds__(BIG_NT, 2) k_big_layer(BigArgs a) {
     const int npk = d * (d + 1) / 2;
     float2* A = a.scratch + (size_t)blockIdx.x * big_scratch_f2(d);
     float2* V = A + (size_t)d * d;
+    float2* A0 = V + (size_t)d * d;
     const float* __restrict__ P = a.Pk;
     const float inv_rho_g = P[P_INV_RHO_G], rho_h_eps = P[P_RHO_H_EPS];
     for (int sig = blockIdx.x; sig < a.B; sig += gridDim.x) {
@@ -255,8 +280,8 @@ __global__ void __launch_bounds__(BIG_NT, 2) k_big_layer(BigArgs a) {
         if (tid == 0) A[n + (size_t)n * d].x += P[P_C0];
         __syncthreads();
         // ---- eigh + eigenvalue map
-        big_jacobi(A, V, d, s, a.status);
-        for (int i = tid; i < d; i += BIG_NT) s.lamp[i] = eig_map(P, A[i + (size_t)i * d].x);
+        big_jacobi(A, V, A0, d, s, a.status);
+        for (int i = tid; i < d; i += BIG_NT) s.lamp[i] = eig_map(P, s.lamp[i]);
         __syncthreads();
         // ---- rebuild G = V diag(l') V^H (lower triangle), residual norm ||G - C||_F, packed store
         float rsq = 0.f;
@@ -300,6 +325,7 @@ k_big_eigh(const float2* __restrict__ Afull, int B, int d, float* evals, float2*
     const int tid = threadIdx.x, npk = d * (d + 1) / 2;
     float2* A = scratch + (size_t)blockIdx.x * big_scratch_f2(d);
     float2* V = A + (size_t)d * d;
+    float2* A0 = V + (size_t)d * d;
     for (int sig = blockIdx.x; sig < B; sig += gridDim.x) {
         const float2* Ag = Afull + (size_t)sig * d * d;
         for (int idx = tid; idx < d * d; idx += BIG_NT) {
@@ -312,9 +338,9 @@ k_big_eigh(const float2* __restrict__ Afull, int B, int d, float* evals, float2*
             if (i != j) A[j + (size_t)i * d] = cconj(v);
         }
         __syncthreads();
-        big_jacobi(A, V, d, s, status);
+        big_jacobi(A, V, A0, d, s, status);
         for (int i = tid; i < d; i += BIG_NT) {
-            const float l = A[i + (size_t)i * d].x;
+            const float l = s.lamp[i];
             if (evals) evals[(size_t)sig * d + i] = l;
             s.lamp[i] = Pk ? eig_map(Pk, l) : l;
         }

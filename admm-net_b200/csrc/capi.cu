@@ -18,6 +18,7 @@
 #include "tc_probe.cu"
 #include "tail_tc.cu"
 #include "big_kernels.cu"
+#include "dc_kernels.cu"
 
 using namespace admmnet;
 
@@ -55,8 +56,8 @@ static cudaError_t ensure_smem(F* func, int bytes) {
 // Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline / launch count).
 // Process-global (guarded by a mutex); off by default (then the only cost is one branch per launch).
 namespace prof {
-enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, ARROW, BIG, NKINDS };
-static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge", "k_arrow", "k_big_layer"};
+enum Kind { HEAD = 0, QL, ROT, TAIL, MISC, CLASSIC, PEAK, HEAD2, MERGE, ARROW, BIG, DC, NKINDS };
+static const char* kNames[NKINDS] = {"k_head", "k_ql", "k_rot", "k_tail", "misc", "k_classic", "k_peak_search", "k_head2", "k_merge", "k_arrow", "k_big_layer", "k_dc"};
 struct Rec { int kind; cudaEvent_t a, b; };
 static bool on = false;
 static std::mutex mu;               // launches may come from several host threads while profiling is on
@@ -234,15 +235,13 @@ int check_net_args(int B, int& chunk, int n, int K, int& rcap) {
     return 0;
 }
 
-// Divide & conquer plan for the tridiagonal eigenproblem: L levels -> 2^L blocks (ADMMNET_DC=L, default 0 = plain
-// QL).  Measured on B200 (131072 signals x 9 layers): L=3 cuts k_ql 292 -> 85 ms and k_rot 468 -> 157 ms per step, but
-// the fp64-flavoured secular solves of k_merge cost 1690 ms, so the path is validated (all parity tests pass with
-// ADMMNET_DC=1..3) but off by default until the merge is rewritten in fp32 with Loewner-corrected z.
-// Small batches are the exception: there the single-thread QL chain (8.5k dependent rotations, ~1.7 ms per layer) is
-// pure latency, D&C shortens it 7x and the merges are cheap in absolute terms, so B <= 1024 defaults to L = 3.
+// Legacy divide & conquer plan for the QL form of the tridiagonal solver: L levels -> 2^L blocks solved by k_ql/k_rot
+// and glued by k_merge (ADMMNET_DC=L with ADMMNET_DCK=0; default 0 = plain QL).  Parity-green (tests run it), but its
+// fp64-flavoured secular solves cost more than the rotations they save (1690 ms against 760 ms per step of 131072
+// signals x 9 layers); the fused fp32 kernel k_dc (csrc/dc_kernels.cu) superseded it, also for small batches.
 inline int dc_levels(int d, int B) {
     static const int env = getenv("ADMMNET_DC") ? atoi(getenv("ADMMNET_DC")) : -1;
-    int L = env < 0 ? (B <= 1024 ? 3 : 0) : (env > 3 ? 3 : env);
+    int L = env < 0 ? 0 : (env > 3 ? 3 : env);
     while (L > 0 && (d >> L) < 8) --L;        // blocks of at least 8
     return L;
 }
@@ -285,10 +284,47 @@ int launch_head2(const Ws& w, int B, int d, cudaStream_t st, const int* skip = n
     return 0;
 }
 
-// the three eigen-solver launches after the tridiagonal form is in the workspace
+// Per-phase clock counters of k_dc (CTA 0, summed over launches) when ADMMNET_DC_PROF=1: a tuning aid.
+static long long* dc_prof_buffer() {
+    static long long* buf = [] {
+        long long* p = nullptr;
+        if (getenv("ADMMNET_DC_PROF") && atoi(getenv("ADMMNET_DC_PROF")) != 0) {
+            if (cudaMalloc(&p, DCP_N * sizeof(long long)) != cudaSuccess) p = nullptr;
+            else cudaMemset(p, 0, DCP_N * sizeof(long long));
+        }
+        return p;
+    }();
+    return buf;
+}
+// the eigen-solver launches after the tridiagonal form is in the workspace
 int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk, int with_c, float2* U_out,
                     float* lamp_out, int* status, cudaStream_t st, cudaStream_t qst = nullptr,
-                    cudaEvent_t ev_in = nullptr, cudaEvent_t ev_out = nullptr, const int* skip = nullptr) {
+                    cudaEvent_t ev_in = nullptr, cudaEvent_t ev_out = nullptr, const int* skip = nullptr,
+                    bool lone = true) {
+    // Tridiagonal eigenproblem.  Two forms, both parity-tested (tests/test_gpu_parity.py):
+    //   * k_dc (csrc/dc_kernels.cu): fused fp32 divide & conquer, one CTA per signal.  Throughput bound; it has no
+    //     serial chain, so it wins whenever the launch stands alone - a call of a single chunk (B <= chunk: latency and
+    //     small-batch mode, B = 1: 9.8 -> 4.4 ms for K = 10) and the eigh tap of the training path
+    //     (measured on B200, d = 101: 0.12 ms against 0.93 ms at B = 1, 1.14 against 4.9 at B = 2368, 7.6 against 9.4
+    //     at B = 16384).
+    //   * k_ql (fp64 scalar QL chain, one thread per signal, pure latency: 4.1 ms whatever the batch) + k_rotf.  In a
+    //     many-chunk forward k_ql runs on the priority lane underneath the other chunk's kernels, which makes this
+    //     pair 6 % faster end to end (84.0k against 79.0k signals/s), so chunks of a larger batch keep it.
+    // ADMMNET_DCK = 1 / 0 forces one form; ADMMNET_DC = 1..3 adds k_merge levels to the QL form (legacy).
+    static const int dck_env = getenv("ADMMNET_DCK") ? atoi(getenv("ADMMNET_DCK")) : -1;
+    const bool use_dck = dck_env >= 0 ? dck_env != 0 : lone;
+    const float* zfinal = w.Zr;
+    if (use_dck) {
+        DcArgs da;
+        da.dT = w.dT; da.eT = w.eT; da.lam = w.lam; da.Zt = w.Zr; da.status = status; da.skip = skip;
+        da.prof = dc_prof_buffer();
+        da.B = B; da.d = d; da.ldz = 4 * ((d + 3) / 4);
+        const size_t sm = dc_smem_bytes(d, da.ldz);
+        CK(ensure_smem(k_dc, (int)sm));
+        prof::Scope pscope(prof::DC, st);
+        k_dc<<<B, DCK_NT, sm, st>>>(da);
+        CK(cudaGetLastError());
+    } else {
     const bool side = qst != nullptr;
     if (side) {   // k_ql on a high-priority side stream: it is latency bound and co-resides with other kernels
         CK(cudaEventRecord(ev_in, st));
@@ -321,7 +357,6 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(cudaGetLastError());
     }
     // divide & conquer merges, leaves -> root; Z ping-pongs between the two scratch buffers
-    const float* zfinal = w.Zr;
     {
         const TearSpec ts = dc_tears(d, B);
         const int L = dc_levels(d, B);
@@ -351,6 +386,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
             cur ^= 1;
         }
         zfinal = zb[cur];
+    }
     }
     {
         TailArgs t;
@@ -557,7 +593,8 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     }
     CK(cudaGetLastError());
     if (int e = launch_head2(w, Bc, d, st, skip)) return e;
-    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out, skip);
+    return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out, skip,
+                           /*lone=*/B <= chunk);
 }
 
 extern "C" int admmnet_reset_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream) {
@@ -908,6 +945,16 @@ extern "C" int admmnet_tail_tc_profile_read(long long* host16) {
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host16, p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     CK(cudaMemset(p, 0, 16 * sizeof(long long)));
+    return 0;
+}
+
+extern "C" int admmnet_dc_profile_read(long long* host128) {
+    if (!host128) return fail(ADMMNET_ERR_ARG, "null pointer");
+    long long* p = dc_prof_buffer();
+    if (!p) { memset(host128, 0, DCP_N * sizeof(long long)); return 0; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host128, p, DCP_N * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p, 0, DCP_N * sizeof(long long)));
     return 0;
 }
 

@@ -187,6 +187,10 @@ int admmnet_tail_tc_smem_bytes(int d);
 /* tuning aid: with ADMMNET_TC_PROF=1 in the environment k_tail_tc's CTA 0 accumulates clock cycles per phase
  * (13 counters, csrc/tail_tc.cu enum TcPhase; the last one counts signals); reads and clears them. */
 int admmnet_tail_tc_profile_read(long long* host16);
+/* tuning aid: with ADMMNET_DC_PROF=1 k_dc's CTA 0 accumulates clock cycles per (level, phase) of the divide & conquer
+ * tridiagonal solver (csrc/dc_kernels.cu: counters 8*level+phase, secular iterations/warps at 72+level / 80+level,
+ * signals at 96); reads and clears the 128 counters. */
+int admmnet_dc_profile_read(long long* host128);
 int admmnet_tc_gemm_probe(const float* A, const float* B, const float* D0, int N, int K, int flags, float* out,
                           void* stream);
 

@@ -45,7 +45,8 @@ def main():
     lo, hi = shard_range(3000, rank, world)
     net.chunk = 512
     phi = sharded_forward(net, y[lo:hi], b[lo:hi], s[lo:hi], "global")
-    full = net(y.cuda(), b.cuda(), s.cuda())[lo:hi]
+    with torch.no_grad():
+        full = net(y.cuda(), b.cuda(), s.cuda())[lo:hi]
     e3 = rel_err(phi.cpu().numpy(), full.cpu().numpy()).max()
     print(f"rank {rank} B=3000 global-scope (2 ranks) vs single-GPU whole batch: {e3:.2e}")
     ok &= e3 < 2e-5

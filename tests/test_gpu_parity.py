@@ -184,7 +184,7 @@ def test_forward_general_path_at_layer0_when_shortcut_declines(pkg):
     net.load_state_dict(sd)
     y, b, s = (torch.from_numpy(z[k]).clone() for k in ("y", "b", "sigma"))
     y[2, 17] = 0
-    got = net(y, b, s).numpy()
+    got = net(y, b, s).detach().numpy()      # grad enabled: the result carries a grad_fn, like the reference's
     ref = net_oracle.forward(sd, y, b, s, 10, 10, K).numpy()
     assert rel_err(got, ref).max() < 1e-4
 
@@ -283,21 +283,22 @@ def test_forward_vs_oracle_seeded_batch_and_scopes(pkg):
 
 
 def test_ql_and_divide_and_conquer_paths_agree(pkg):
-    """Launches of more than 1024 signals use plain QL for the tridiagonal eigenproblem, smaller ones the
-    divide & conquer merge kernel (capi.cu::dc_levels).  Same batch, same whole-batch norm scope, two scratch
-    chunk sizes -> both paths; they must agree with each other and with the oracle."""
+    """A call of ONE chunk solves the tridiagonal eigenproblem with the fused fp32 divide & conquer kernel (k_dc,
+    csrc/dc_kernels.cu), a call of several chunks with the QL pair k_ql + k_rotf (capi.cu::launch_eig_tail).  Same
+    batch, same whole-batch norm scope, two scratch chunk sizes -> both paths; they must agree with each other and
+    with the oracle."""
     from oracle import net_oracle, signals
     torch.manual_seed(11)
     net = pkg.PhiEstADMMNet(10, 10, 3, 6).eval()
     y, b, s, _ = signals.generate(1280, seed=29)
     yt, bt, st = (torch.from_numpy(a) for a in (y, b, s))
-    net.chunk = 4096                                   # one launch of 1280 signals: QL path
+    net.chunk = 4096                                   # one launch of 1280 signals: k_dc
     with torch.no_grad():
         phi_ql = net(yt, bt, st).numpy()
-    net.chunk = 320                                    # four launches of 320 signals: D&C path
+    net.chunk = 320                                    # four launches of 320 signals: k_ql + k_rotf
     with torch.no_grad():
         phi_dc = net(yt, bt, st).numpy()
-    assert rel_err(phi_dc, phi_ql).max() < 3e-5
+    assert rel_err(phi_dc, phi_ql).max() < 3e-5         # (the names follow the chunk sizes above the other way round)
     ref = net_oracle.forward(net.state_dict(), yt, bt, st, 10, 10, 6).numpy()
     assert rel_err(phi_ql, ref).max() < PHI_TOL
     assert rel_err(phi_dc, ref).max() < PHI_TOL
@@ -307,7 +308,7 @@ def test_benchmarked_path_multichunk_lanes_against_oracle(pkg):
     """the configuration bench.py times — several scratch chunks of MORE than 1024 signals
     (plain-QL path, not divide & conquer), chunk lanes on, the persistent tail kernel on both scratch slots, whole-
     batch norm scope — against the oracle run on the whole batch.  6000 signals = 3 chunks of 2000 over 2 lanes
-    (slot 0 twice, slot 1 once), perturbed weights, K = 10."""
+    (slot 0 twice, slot 1 once), perturbed weights, K = 10.  Several chunks: the QL pair solves the tridiagonal problems."""
     from oracle import net_oracle, signals
     z, sd = load_net_case("pert_k10")
     net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
@@ -321,7 +322,7 @@ def test_benchmarked_path_multichunk_lanes_against_oracle(pkg):
     ref = net_oracle.forward(sd, yt, bt, st, 10, 10, 10).numpy()
     err = rel_err(phi, ref)
     assert err.max() < PHI_TOL, (err.max(), int(err.argmax()))
-    # ragged last chunk on the other slot: 4500 = 2000 + 2000 + 500 (the 500-signal launch takes the D&C path)
+    # ragged last chunk on the other slot: 4500 = 2000 + 2000 + 500
     with torch.no_grad():
         phi2 = net(yt[:4500].cuda(), bt[:4500].cuda(), st[:4500].cuda()).cpu().numpy()
     ref2 = net_oracle.forward(sd, yt[:4500], bt[:4500], st[:4500], 10, 10, 10).numpy()
@@ -628,20 +629,23 @@ def test_admmnet_full_module_matches_reference_golden(pkg):
     np.testing.assert_allclose(t3.cpu().numpy(), z["tau"][:5], atol=2e-6, rtol=1e-5)
 
 
-@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILTC", "ADMMNET_LANES", "ADMMNET_TRD=1"])
+@pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILTC", "ADMMNET_LANES", "ADMMNET_TRD=1",
+                                    "ADMMNET_DCK", "ADMMNET_DCK=0,ADMMNET_DC=2"])
 def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
     """Every fast path has a plain sibling behind an environment switch (read once per process, hence the
     subprocess): ADMMNET_ARROW=0 dense eigen-solver at layer 0 instead of the arrowhead shortcut, ADMMNET_ROTF=0
     one sweep at a time in the rotation kernel, ADMMNET_TAILTC=0 the SIMT (FFMA2) back-transformation and rebuild
     instead of the tcgen05 kernel, ADMMNET_LANES=0 single stream, ADMMNET_TRD=1 the register-resident
-    tridiagonalisation (opt-in) instead of the staged shared-memory one.  Same inputs, same answer."""
+    tridiagonalisation (opt-in) instead of the staged shared-memory one, ADMMNET_DCK=0 the QL pair instead of the fused
+    divide & conquer kernel this single-chunk call takes by default (and with ADMMNET_DC=2 the legacy k_merge levels
+    on top of it).  Same inputs, same answer."""
     import subprocess
     import sys
     z, sd = load_net_case("pert_k10")
     net = pkg.PhiEstADMMNet(10, 10, 3, 10).eval()
     net.load_state_dict(sd)
     y, b, s = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma"))
-    yy, bb, ss = y.repeat(300, 1), b.repeat(300, 1), s.repeat(300)        # 2100 signals: the large-batch (QL) path
+    yy, bb, ss = y.repeat(300, 1), b.repeat(300, 1), s.repeat(300)        # 2100 signals in one chunk
     with torch.no_grad():
         phi = net(yy, bb, ss).numpy()
     out = str(tmp_path / "phi_alt.npy")
@@ -656,8 +660,9 @@ def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
         "with torch.no_grad():\n"
         f"    np.save({out!r}, net(y.repeat(300, 1), b.repeat(300, 1), s.repeat(300)).numpy())\n")
     env = dict(os.environ)
-    name, _, val = switch.partition("=")
-    env[name] = val or "0"
+    for item in switch.split(","):
+        name, _, val = item.partition("=")
+        env[name] = val or "0"
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
     phi_alt = np.load(out)
     assert rel_err(phi, phi_alt).max() < 3e-5

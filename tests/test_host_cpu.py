@@ -321,3 +321,25 @@ def test_fused_sweep_schedule_equals_sequential_sweeps_for_every_range_pair():
                     n_pairs += 1
                     n_rule += would_pair(mA, cntA, mB, cntB)
     assert n_pairs == 1296 and 0 < n_rule < n_pairs
+
+
+def test_dc_emulation_tridiagonal_eigensolver_is_accurate_in_fp32():
+    """The algorithm of csrc/dc_kernels.cu (fused divide & conquer with every off-diagonal torn, secular roots in
+    shifted coordinates, Gu-Eisenstat vectors, xLAED2 deflation) emulated in float32 (tests/dc_emulation.py):
+    residual, orthogonality and eigenvalues at rounding level on random, clustered, graded, Wilkinson and degenerate
+    tridiagonals - the cases where a fp32 solver without the z re-derivation loses orthogonality."""
+    from tests.dc_emulation import check
+    rng = np.random.default_rng(0)
+    cases = {
+        "random": (rng.normal(size=101) * 3, rng.normal(size=100)),
+        "wilkinson": (np.abs(np.arange(41) - 20.0), np.ones(40)),
+        "graded": (10.0 ** -np.linspace(0, 6, 64), 10.0 ** -np.linspace(0, 6, 64)[:-1] * 0.5),
+        "clustered": (np.ones(101) + 1e-5 * rng.normal(size=101), 1e-3 * rng.normal(size=100)),
+        "toeplitz": (2 * np.ones(33), -np.ones(32)),
+        "some_zero_e": (rng.normal(size=101), rng.normal(size=100) * (rng.random(100) > 0.3)),
+        "identity": (np.ones(17), np.zeros(16)),
+        "three": (rng.normal(size=3), rng.normal(size=2)),
+    }
+    for name, (dT, eT) in cases.items():
+        res, orth, ev, _ = check(dT, eT)
+        assert res < 2e-6 and orth < 2e-6 and ev < 2e-6, (name, res, orth, ev)

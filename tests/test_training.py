@@ -149,6 +149,48 @@ def test_train_step_lowers_the_loss_gpu():
     assert float((fast - slow).abs().max() / slow.abs().max()) < 1e-4
 
 
+@pytest.mark.gpu
+def test_eval_mode_forward_is_differentiable_like_the_reference_gpu():
+    """test/test_time_net.py:94-100 calls the model in eval() with grad enabled and gets a differentiable phi.  Here the
+    values come from the fused kernels and the graph is rebuilt when backward is called (_FusedForward): same values as
+    no_grad, a grad_fn on the result, and the gradients of the train()-mode graph; ADMMNet likewise."""
+    from admmnet_b200.autograd import PhiAlignmentLoss
+    z, sd, _ = _load()
+    K = int(z["K"])
+    y, b, s, pt = (torch.from_numpy(z[k]).cuda() for k in ("y", "b", "sigma", "phi_true"))
+    crit = PhiAlignmentLoss()
+    m_eval, m_train = _model(sd, K, "cuda").eval(), _model(sd, K, "cuda").train()
+    phi = m_eval(y, b, s)
+    assert phi.requires_grad and phi.grad_fn is not None
+    with torch.no_grad():
+        assert torch.equal(phi.detach(), m_eval(y, b, s))
+    crit(phi, pt)[0].backward()
+    crit(m_train(y, b, s), pt)[0].backward()
+    live = 0
+    for (n1, p1), (_, p2) in zip(m_eval.named_parameters(), m_train.named_parameters()):
+        assert (p1.grad is None) == (p2.grad is None), n1
+        if p1.grad is not None:
+            live += 1
+            assert float((p1.grad - p2.grad).abs().max()) <= 2e-3 * (float(p2.grad.abs().max()) + 1e-12), n1
+    assert live > 40
+    # gradient with respect to an input
+    yg = y.clone().requires_grad_(True)
+    m_eval(yg, b, s).abs().sum().backward()
+    assert yg.grad is not None and float(yg.grad.abs().max()) > 0
+    # host tensors in, host tensors out, still differentiable
+    assert m_eval(y.cpu(), b.cpu(), s.cpu()).requires_grad
+    # ADMMNet: all four outputs differentiable in eval mode
+    import admmnet_b200
+    torch.manual_seed(1)
+    net = admmnet_b200.ADMMNet(10, 10, 3, 3).cuda().eval()
+    tau, f, conf, phi4 = net(y, b, s)
+    (tau.sum() + f.sum() + conf.sum() + phi4.abs().sum()).backward()
+    assert net.peakSearchLayer.tau_regressor[0][0].weight.grad is not None and net.phiLayers[0].rho.grad is not None
+    with torch.no_grad():
+        t2, f2, c2, p2 = net(y, b, s)
+    assert torch.equal(p2, phi4.detach()) and float((t2 - tau.detach()).abs().max()) < 1e-5
+
+
 # ------------------------------------------------------------------ dataset / checkpoint formats (SURVEY §8f rank 4)
 def _fake_split(d, n=6, nn=100, L=3, with_phi=True):
     rng = np.random.default_rng(0)
