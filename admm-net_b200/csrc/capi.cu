@@ -815,8 +815,39 @@ extern "C" int admm_classic_forward(const void* y, const void* b, int in_is_c128
     cudaStream_t st = (cudaStream_t)stream;
     prof::Scope pscope(prof::CLASSIC, st);
     static const int gl_env = getenv("ADMMNET_CLASSIC_GL") ? atoi(getenv("ADMMNET_CLASSIC_GL")) : 0;
-    // measured on B200 at batch 65536, n = 100 (tools/classic_ab.py): 5 iterations 32 lanes 95 us / 16 lanes 115 us /
-    // 8 lanes 167 us; 100 iterations 665 / 503 / 536 us -> 32 lanes per signal for short runs, 16 for long ones
+    // complex64 input, n even (16-byte bulk-copy granularity), n <= 104: the persistent streaming form
+    // (ADMMNET_CLASSIC_P=0 or an explicit ADMMNET_CLASSIC_GL select the plain kernels)
+    static const bool use_p = !(getenv("ADMMNET_CLASSIC_P") && atoi(getenv("ADMMNET_CLASSIC_P")) == 0);
+    static const int pv = getenv("ADMMNET_CLASSIC_PV") ? atoi(getenv("ADMMNET_CLASSIC_PV")) : 0;
+    if (use_p && !gl_env && !in_is_c128 && n <= 104 && n % 2 == 0 && (((uintptr_t)y | (uintptr_t)b | (uintptr_t)phi_out) & 15) == 0) {
+        int dev = 0, nsm = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+#define CLASSIC_P_LAUNCH(GL, MAXE, NT, MINB)                                                                        \
+        {                                                                                                           \
+            const int S = classic_p_tile<GL, NT>(), ntiles = (B + S - 1) / S, cap = nsm * MINB;                     \
+            const size_t sm = classic_p_smem_bytes<GL, NT>(n);                                                      \
+            CK(ensure_smem(k_classic_p<GL, MAXE, NT, MINB>, (int)sm));                                              \
+            k_classic_p<GL, MAXE, NT, MINB><<<ntiles < cap ? ntiles : cap, NT, sm, st>>>(                           \
+                (const float2*)y, (const float2*)b, B, n, rho, n_iter, (double2*)phi_out);                          \
+        }
+        // tile / occupancy variants (tools/classic_ab.py; batch 65536, n = 100, 5 / 100 iterations, us per launch):
+        //   0: 8 lanes per signal, 256 threads, one CTA per SM (default)   64.7 / 355
+        //   1: 16 lanes, 256 threads, two CTAs per SM                      65.2 / 483
+        //   2: 8 lanes, 128 threads, two CTAs per SM                       62.8 / 395
+        //   3: 16 lanes, 512 threads, one CTA per SM                       66.5 / 460
+        // against 94 / 504 for the best plain kernel: the short run is memory bound whatever the tiling, the long one
+        // fp64 bound and prefers the fewest shuffle steps and idle lanes (8 lanes x 13 elements for n = 100)
+        if (pv == 1) CLASSIC_P_LAUNCH(16, 7, 256, 2)
+        else if (pv == 2) CLASSIC_P_LAUNCH(8, 13, 128, 2)
+        else if (pv == 3) CLASSIC_P_LAUNCH(16, 7, 512, 1)
+        else CLASSIC_P_LAUNCH(8, 13, 256, 1)
+#undef CLASSIC_P_LAUNCH
+        CK(cudaGetLastError());
+        return 0;
+    }
+    // plain kernels (complex128 input, odd n, n > 104), measured on B200 at batch 65536, n = 100: 5 iterations
+    // 32 lanes 94 us / 16 lanes 114 us / 8 lanes 167 us; 100 iterations 504 / 506 / 610 us
     const int gl = (gl_env == 8 && n <= 104) ? 8 : (gl_env == 16 && n <= 112) ? 16 : (gl_env == 32) ? 32
                    : ((n_iter > 20 && n <= 112) ? 16 : 32);
     const int grid = (int)(((long long)B * gl + 255) / 256);      // one group of gl lanes per signal

@@ -75,7 +75,9 @@ class GraphedTrainStep:
     run eagerly.  Inputs are copied into static buffers; shapes are fixed (a ragged tail batch runs through the
     eager `train_step`).  The optimizer must be capturable (make_optimizer(..., capturable=True)).  The three eager
     warm-up steps PyTorch's capture needs are run on a snapshot of the model/optimizer state, which is restored
-    before the capture, so graph mode takes exactly the same parameter trajectory as eager mode."""
+    before the capture, so graph mode takes exactly the same parameter trajectory as eager mode.  The learning rate
+    is a capture-time constant (a Python float in the param groups): re-capture after `scheduler.step()` changes it;
+    `fit` / `fit_admmnet` therefore use the eager `train_step`."""
 
     def __init__(self, model, criterion, optimizer, example, max_norm=1.0, group=None):
         import copy
@@ -91,11 +93,36 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         model.load_state_dict(snap_m)
-        optimizer.load_state_dict(snap_o)
+        self._restore_optimizer(optimizer, snap_o)
         optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
+
+    @staticmethod
+    def _restore_optimizer(optimizer, snap):
+        """Put the optimizer back to the snapshot IN PLACE.  The state tensors the warm-up created (step, exp_avg,
+        exp_avg_sq) must stay alive: were they dropped (optimizer.load_state_dict of a fresh snapshot), the captured
+        step would lazily re-create and zero them inside the graph, i.e. on every replay."""
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        with torch.no_grad():
+            for idx, p in enumerate(params):
+                st = optimizer.state.get(p)
+                if not st:
+                    continue
+                old = snap["state"].get(idx)
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
+                    elif old is not None and k in old:
+                        st[k] = old[k]
+        for g, og in zip(optimizer.param_groups, snap["param_groups"]):
+            for k, v in og.items():
+                if k != "params":
+                    g[k] = v
 
     def _body(self):
         y, b, sigma, phi_true = self.static

@@ -271,7 +271,9 @@ def test_forward_vs_oracle_seeded_batch_and_scopes(pkg):
     with torch.no_grad():
         phi_c = net(yt, bt, st)
     assert rel_err(phi_c.numpy(), ref.numpy()).max() < PHI_TOL
-    assert rel_err(phi_c.numpy(), phi.cpu().numpy()).max() < 1e-5
+    # (one chunk: fused divide & conquer tridiagonal solver, several chunks: the QL pair - two fp32 solvers agree to
+    #  the forward's rounding floor, DESIGN.md accuracy budget, not to 1e-5)
+    assert rel_err(phi_c.numpy(), phi.cpu().numpy()).max() < 3e-5
     # norm_scope='chunk': independent chunks == the reference run per chunk
     net.norm_scope = "chunk"
     net.chunk = 32
