@@ -38,6 +38,7 @@ _PROTOS = {
     "admmnet_profile_kind_name": (C.c_char_p, [_i]),
     "admmnet_profile_end": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "admmnet_tail_tc_smem_bytes": (_i, [_i]),
+    "admmnet_tail_tc_mma_flops": (_d, [_i]),
     "admmnet_tail_tc_profile_read": (_i, [_vp]),
     "admmnet_dc_profile_read": (_i, [_vp]),
     "admmnet_tc_gemm_probe": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

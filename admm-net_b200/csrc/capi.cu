@@ -245,9 +245,19 @@ inline int dc_levels(int d, int B) {
     while (L > 0 && (d >> L) < 8) --L;        // blocks of at least 8
     return L;
 }
-inline TearSpec dc_tears(int d, int B) {
+// Hybrid plan for many-chunk batches (ADMMNET_HYB = levels, default below): k_ql + k_rotf solve the 2^L blocks of the torn
+// tridiagonal (half / quarter length sweeps: the latency-bound QL chain and the rotation count shrink accordingly) and
+// k_dc runs only the top L merge levels.
+inline int hyb_levels(int d) {
+    static const int env = getenv("ADMMNET_HYB") ? atoi(getenv("ADMMNET_HYB")) : 0;
+    int L = env < 0 ? 0 : (env > 2 ? 2 : env);
+    while (L > 0 && (d >> L) < 16) --L;
+    return L;
+}
+inline TearSpec dc_tears(int d, int B, int hyb = 0) {
     TearSpec ts;
-    const int L = dc_levels(d, B), nb = 1 << L;
+    ts.absconv = hyb > 0 ? 1 : 0;
+    const int L = hyb > 0 ? hyb : dc_levels(d, B), nb = 1 << L;
     ts.n = nb - 1;
     for (int q = 0; q < ts.n; ++q) ts.pos[q] = (int)(((long long)(q + 1) * d) / nb);
     return ts;
@@ -313,17 +323,25 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
     // ADMMNET_DCK = 1 / 0 forces one form; ADMMNET_DC = 1..3 adds k_merge levels to the QL form (legacy).
     static const int dck_env = getenv("ADMMNET_DCK") ? atoi(getenv("ADMMNET_DCK")) : -1;
     const bool use_dck = dck_env >= 0 ? dck_env != 0 : lone;
+    const int hyb = use_dck ? 0 : hyb_levels(d);
     const float* zfinal = w.Zr;
-    if (use_dck) {
+    auto launch_dc = [&](int nhyb, const TearSpec& ts) -> int {
         DcArgs da;
         da.dT = w.dT; da.eT = w.eT; da.lam = w.lam; da.Zt = w.Zr; da.status = status; da.skip = skip;
         da.prof = dc_prof_buffer();
         da.B = B; da.d = d; da.ldz = 4 * ((d + 3) / 4);
+        da.beta_in = w.rho; da.nhyb = nhyb; da.ntear = nhyb ? ts.n : 0; da.tear_stride = DC_MAXTEAR;
+        for (int q = 0; q < 7; ++q) da.tear_pos[q] = q < ts.n ? ts.pos[q] : 1;
         const size_t sm = dc_smem_bytes(d, da.ldz);
         CK(ensure_smem(k_dc, (int)sm));
         prof::Scope pscope(prof::DC, st);
         k_dc<<<B, DCK_NT, sm, st>>>(da);
         CK(cudaGetLastError());
+        return 0;
+    };
+    if (use_dck) {
+        TearSpec none; none.n = 0; none.absconv = 0;
+        if (int e = launch_dc(0, none)) return e;
     } else {
     const bool side = qst != nullptr;
     if (side) {   // k_ql on a high-priority side stream: it is latency bound and co-resides with other kernels
@@ -337,7 +355,7 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(ensure_smem(k_ql, (int)sm));
         prof::Scope pscope(prof::QL, st);
         k_ql<<<(B + QL_THREADS - 1) / QL_THREADS, QL_THREADS, sm, st>>>(w.dT, w.eT, B, d, w.lam, w.rot, rcap, w.nrot,
-                                                                         status, dc_tears(d, B), w.rho, skip);
+                                                                         status, dc_tears(d, B, hyb), w.rho, skip);
         CK(cudaGetLastError());
     }
     if (side) {
@@ -356,8 +374,11 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         k_rot<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
         CK(cudaGetLastError());
     }
-    // divide & conquer merges, leaves -> root; Z ping-pongs between the two scratch buffers
-    {
+    if (hyb > 0) {
+        // the top merge levels in the fused kernel (in place: it stages Z^T in shared memory first)
+        if (int e = launch_dc(hyb, dc_tears(d, B, hyb))) return e;
+    } else {
+        // legacy divide & conquer merges, leaves -> root; Z ping-pongs between the two scratch buffers
         const TearSpec ts = dc_tears(d, B);
         const int L = dc_levels(d, B);
         float* zb[2] = {w.Zr, w.Zr2};
@@ -987,6 +1008,21 @@ extern "C" int admmnet_dc_profile_read(long long* host128) {
     CK(cudaMemcpy(host128, p, DCP_N * sizeof(long long), cudaMemcpyDeviceToHost));
     CK(cudaMemset(p, 0, DCP_N * sizeof(long long)));
     return 0;
+}
+
+// tcgen05.mma work k_tail_tc issues per signal for matrix order d (flops, 2 per multiply-add, every 3xTF32 split term
+// counted): per compact-WY block with window K2 = 2 (dp - a0): GEMM 1 = M 128 x N (96 + 48) x K K2, GEMM 2 = six
+// chains M 128 x N K2 x K 24; rebuild = twelve chains M 128 x N dp x K dp.  0 when the kernel does not serve d.
+extern "C" double admmnet_tail_tc_mma_flops(int d) {
+    TailTcPlan plan;
+    if (!tail_tc_plan(d, plan)) return 0.0;
+    double f = 0.0;
+    for (int j = 0; j < plan.nblk; ++j) {
+        const double K2 = 2.0 * (plan.dp - plan.a0[j]);
+        f += 2.0 * 128.0 * K2 * (96.0 + 48.0) + 6.0 * 2.0 * 128.0 * K2 * TC_NB;
+    }
+    f += 12.0 * 2.0 * 128.0 * (double)plan.dp * (double)plan.dp;
+    return f;
 }
 
 // shared-memory bytes of the tensor-core tail kernel for matrix order d, or -1 when d is outside its range (then the

@@ -37,6 +37,12 @@ struct DcArgs {
     const int* skip;
     long long* prof;        // tuning aid (nullptr: off)
     int B, d, ldz;
+    // hybrid form: the lower levels were solved by k_ql + k_rotf on the 2^nhyb blocks of a torn T (TearSpec with
+    // absconv = 1); Zt holds their block-diagonal Q^T, lam their eigenvalues, beta_in[sig][q] the torn off-diagonals at
+    // rows tear_pos[q].  Only the top nhyb merge levels run here.  nhyb = 0: everything from 1 x 1 leaves.
+    const double* beta_in;
+    int nhyb, ntear, tear_stride;
+    int tear_pos[7];
 };
 __host__ __device__ inline size_t dc_smem_bytes(int d, int ldz) {
     return (size_t)2 * d * ldz * sizeof(float) + (size_t)21 * 128 * sizeof(float) + 7 * 64 * sizeof(float) + 80 * sizeof(int);
@@ -154,25 +160,36 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
         tlast = tnow;                                         \
     }
 
-    // ---- leaves: every off-diagonal is a tear
-    if (tid < d) {
-        const float di = a.dT[(size_t)tid * a.B + sig];
-        const float e_own = tid < d - 1 ? a.eT[(size_t)tid * a.B + sig] : 0.f;
-        const float e_prev = tid > 0 ? a.eT[(size_t)(tid - 1) * a.B + sig] : 0.f;
-        lamv[tid] = di - fabsf(e_prev) - fabsf(e_own);
-        es[tid] = e_own;
-    }
-    for (int c = wid; c < d; c += DCK_NT / 32)
-        for (int x = lane; x < ldz; x += 32) {
-            Qa[c * ldz + x] = (c == x) ? 1.f : 0.f;
-            Qb[c * ldz + x] = 0.f;      // a column's coordinates outside its own block are read as zeros by every later merge
+    if (a.nhyb == 0) {
+        // ---- leaves: every off-diagonal is a tear
+        if (tid < d) {
+            const float di = a.dT[(size_t)tid * a.B + sig];
+            const float e_own = tid < d - 1 ? a.eT[(size_t)tid * a.B + sig] : 0.f;
+            const float e_prev = tid > 0 ? a.eT[(size_t)(tid - 1) * a.B + sig] : 0.f;
+            lamv[tid] = di - fabsf(e_prev) - fabsf(e_own);
+            es[tid] = e_own;
         }
+        for (int c = wid; c < d; c += DCK_NT / 32)
+            for (int x = lane; x < ldz; x += 32) {
+                Qa[c * ldz + x] = (c == x) ? 1.f : 0.f;
+                Qb[c * ldz + x] = 0.f;      // a column's coordinates outside its own block are read as zeros by every later merge
+            }
+    } else {
+        // ---- blocks solved by the QL pair: eigenvalues, block-diagonal Q^T and the torn off-diagonals from global memory
+        if (tid < d) { lamv[tid] = a.lam[(size_t)sig * d + tid]; es[tid] = 0.f; }
+        for (int idx = tid; idx < d * ldz / 4; idx += DCK_NT) {
+            reinterpret_cast<float4*>(Qa)[idx] = reinterpret_cast<const float4*>(Zg)[idx];
+            reinterpret_cast<float4*>(Qb)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (tid < a.ntear) es[a.tear_pos[tid] - 1] = (float)a.beta_in[(size_t)sig * a.tear_stride + tid];
+    }
     int nl = 0;
     while ((1 << nl) < d) ++nl;
     bool bad = false;
     __syncthreads();
 
-    for (int lev = 1; lev <= nl; ++lev) {
+    for (int lev = a.nhyb ? nl - a.nhyb + 1 : 1; lev <= nl; ++lev) {
         const int nb = 1 << (nl - lev);
         const bool top = lev == nl;
         // ---- P0: block tables of the level

@@ -621,6 +621,8 @@ k_tridiag(const float2* __restrict__ Afull, int B, int d, int ld, float2* V, flo
 struct TearSpec {
     int n;
     int pos[DC_MAXTEAR];
+    int absconv;      // 1: d[p-1] -= |rho|, d[p] -= |rho| (the convention of k_dc's merges: rank-one term 2|rho| z z^T,
+                      //    z = (last row of Q1, sign(rho) first row of Q2)/sqrt(2)); 0: signed rho (k_merge)
 };
 __global__ void __launch_bounds__(QL_THREADS)
 k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, float* __restrict__ lam,
@@ -644,8 +646,9 @@ k_ql(const float* __restrict__ dT, const float* __restrict__ eT, int B, int d, f
     for (int q = 0; q < tears.n; ++q) {
         const int p = tears.pos[q];
         const double rho = E_(p - 1);
-        D_(p - 1) -= rho;
-        D_(p) -= rho;
+        const double sub = tears.absconv ? fabs(rho) : rho;
+        D_(p - 1) -= sub;
+        D_(p) -= sub;
         E_(p - 1) = 0.0;
         if (valid) rho_out[(size_t)sig * DC_MAXTEAR + q] = rho;
     }

@@ -314,6 +314,56 @@ def _time_ms(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def measure_tensor_pipe(pkg, dev, tf32_peak_tflops, Bt=16384, d=101):
+    """Tensor-pipe roofline of k_tail_tc, timed ALONE (inside the forward its CUDA-event time overlaps the other
+    chunk lane's kernels): the f(A) tap (tridiagonalisation, tridiagonal solver, tail) on Bt random Hermitian matrices of
+    the benchmark's order with per-kernel events; executed = every tcgen05.mma flop the kernel issues (3xTF32 split
+    terms included, admmnet_tail_tc_mma_flops), useful = the 12 d^3 flops of the two contractions it replaces
+    (back-transformation 8 d^3 + lower-triangle rebuild 4 d^3)."""
+    from admmnet_b200 import _capi
+    from admmnet_b200.params import pack_state_dict
+    L = _capi.lib()
+    mma = float(L.admmnet_tail_tc_mma_flops(d))
+    if mma == 0.0 or L.admmnet_tail_tc_smem_bytes(d) <= 0:
+        return None
+    torch.manual_seed(0)
+    net = pkg.PhiEstADMMNet(M, N, 3, K_LAYERS)
+    P = pack_state_dict(net.state_dict(), M * N, K_LAYERS).to(dev)
+    X = torch.randn(Bt, d, d, dtype=torch.complex64, device=dev) * (3.0 / d ** 0.5)
+    A = (0.5 * (X + X.transpose(1, 2).conj())).contiguous()
+    del X
+    nb = C.c_size_t()
+    _capi.check(L.admmnet_eigh_workspace_bytes(Bt, d, 0, C.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    G = torch.empty(Bt, d * (d + 1) // 2, dtype=torch.complex64, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def run():
+        _capi.check(L.admmnet_eigh_batched(A.data_ptr(), Bt, d, None, None, G.data_ptr(), P[3].data_ptr(), ws.data_ptr(),
+                                           nb.value, 0, torch.cuda.current_stream().cuda_stream, st.data_ptr()))
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    nk = L.admmnet_profile_kinds()
+    reps = 5
+    L.admmnet_profile_begin()
+    for _ in range(reps):
+        run()
+    ms = (C.c_double * nk)()
+    ln = (C.c_longlong * nk)()
+    _capi.check(L.admmnet_profile_end(ms, ln))
+    names = [L.admmnet_profile_kind_name(i).decode() for i in range(nk)]
+    t_ms = ms[names.index("k_tail")] / reps
+    assert int(st.item()) == 0
+    executed = mma * Bt / (t_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "k_tail_tc (tcgen05.mma kind::tf32, 3xTF32 split, X resident in TMEM)",
+            "ms_per_launch": t_ms, "signals_per_launch": Bt, "mma_flops_per_signal": mma,
+            "achieved": executed, "peak": tf32_peak_tflops, "unit": "TFLOP/s", "frac": executed / tf32_peak_tflops,
+            "useful_tflops": 12.0 * d ** 3 * Bt / (t_ms * 1e-3) / 1e12,
+            "note": "kernel timed alone on the f(A) tap; achieved counts every issued MMA flop, useful the 12 d^3 of the "
+                    "back-transformation and rebuild; peak = TF32 cuBLAS 8192^3 measured in this run"}
+
+
 def measure_extras(pkg, dev):
     """The other BASELINE.json configs, measured on rank 0 after the headline run (not bench lines of their own):
     configs[0] single-signal latency (what results/time/*.txt of the reference publish), configs[1] classical ADMM
@@ -576,6 +626,7 @@ def main():
     tf32_peak_tflops = 2 * 8192 ** 3 / (tf32_best * 1e-3) / 1e12
     torch.backends.cuda.matmul.allow_tf32 = False
     del am, bm
+    tensor_pipe = measure_tensor_pipe(admmnet_b200, dev, tf32_peak_tflops)
     extras = None if args.no_extras else measure_extras(admmnet_b200, dev)
     if extras is not None and global_scope is not None:
         extras["global_scope"] = global_scope
@@ -584,7 +635,7 @@ def main():
     gpu_ms = sum(v["ms_per_step"] for v in kern.values())
     for v in kern.values():
         v["share"] = v["ms_per_step"] / gpu_ms
-    eig = ("k_head", "k_head2", "k_ql", "k_rot", "k_merge", "k_tail")
+    eig = ("k_head", "k_head2", "k_ql", "k_rot", "k_merge", "k_dc", "k_tail")
     eig_launch = sum(kern[k]["launches_per_step"] for k in eig if k in kern)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
     ms_step = ms_total / args.steps
@@ -616,7 +667,7 @@ def main():
                   "how": "FP32: FFMA micro-kernel in this library; TF32: torch.matmul 8192^3 allow_tf32, best of 5; "
                          "bf16 and HBM: MEASURED_PEAKS.json"},
         "roofline": {
-            "bound": "fp32", "kernel": "layer pipeline k_head+k_head2+k_ql+k_rot+k_tail (dominant: %s)" % dom,
+            "bound": "fp32", "kernel": "layer pipeline k_head+k_head2+k_ql+k_rot+k_tail_tc (dominant: %s); the tensor-pipe stage k_tail_tc has its own entry under 'tensor'" % dom,
             "forward_ms_per_step": fwd_ms,
             "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
             "traffic": (TRAFFIC_PER_SIGNAL_LAYER * (K_LAYERS - 2) + TRAFFIC_ARROW_LAYER) * B,
@@ -628,6 +679,7 @@ def main():
                     "live (MEASURED_PEAKS.json has no FP32 figure). launches per step: %d" % eig_launch,
             "hbm": {"achieved_gbs": BYTES_PER_SIGNAL * B / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "peak_source": "measured" if peaks else "fallback"},
+            "tensor": tensor_pipe,
             "kernels": kern},
     }
     if extras is not None:

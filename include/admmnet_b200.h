@@ -184,6 +184,9 @@ int peak_surface_maxima(const double* surface, int B, const double* axis_x, int 
 /* shared-memory bytes of the tensor-core tail kernel (k_tail_tc) for matrix order d; -1: d outside its range
  * (33..104, the SIMT tail kernels serve), 0: switched off with ADMMNET_TAILTC=0 */
 int admmnet_tail_tc_smem_bytes(int d);
+/* tcgen05.mma flops k_tail_tc issues per signal of matrix order d (all 3xTF32 split terms; bench.py's tensor-pipe
+ * figure), 0 when the kernel does not serve d */
+double admmnet_tail_tc_mma_flops(int d);
 /* tuning aid: with ADMMNET_TC_PROF=1 in the environment k_tail_tc's CTA 0 accumulates clock cycles per phase
  * (13 counters, csrc/tail_tc.cu enum TcPhase; the last one counts signals); reads and clears them. */
 int admmnet_tail_tc_profile_read(long long* host16);

@@ -1,12 +1,13 @@
 """Turn the ncu artefacts a gpurun call left in gpurun_out/ into the small text summaries committed here.
-    python profiles/summarize.py <tag> <launches.csv> <full.ncu-rep>
+    python profiles/summarize.py <tag> <launches.csv> <full.ncu-rep> [<more.ncu-rep> ...]
 """
 import collections
 import csv
 import subprocess
 import sys
 
-tag, launches, rep = sys.argv[1:4]
+tag, launches = sys.argv[1:3]
+reps = sys.argv[3:]
 out = open(f"profiles/{tag}_ncu_summary.md", "w")
 # ---- launch list: per-kernel share of the (serialised, cold-cache) device time
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
@@ -29,10 +30,10 @@ out.write("| kernel | launches | total ms | avg ms | share |\n|---|---|---|---|-
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
     out.write(f"| {k} | {cnt[k]} | {v:.1f} | {v / cnt[k]:.3f} | {100 * v / T:.1f} % |\n")
 # ---- full capture: key metrics per kernel
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h, units, data = rr[0], rr[1], rr[2:]
-I = {n: i for i, n in enumerate(h)}
+def load(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    return rr[0], rr[1], rr[2:]
 want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -50,13 +51,16 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 # one launch per kernel name: the longest one (layer 0 launches the general kernels too, but there they return at
 # once for every signal the arrowhead shortcut handled)
 best = {}
-for r in data:
-    name = r[I["Kernel Name"]].split("(")[0].replace("void ", "")
-    dur = float(r[I["gpu__time_duration.sum"]].replace(",", ""))
-    if name not in best or dur > best[name][0]:
-        best[name] = (dur, r)
-out.write(f"\n# {tag}: `ncu --set full --clock-control none` (one launch per kernel, 4096 signals per launch)\n")
-for name, (_, r) in best.items():
+for rep in reps:
+    h, units, data = load(rep)
+    I = {n: i for i, n in enumerate(h)}
+    for r in data:
+        name = r[I["Kernel Name"]].split("(")[0].replace("void ", "")
+        dur = float(r[I["gpu__time_duration.sum"]].replace(",", ""))
+        if name not in best or dur > best[name][0]:
+            best[name] = (dur, r, I, units)
+out.write(f"\n# {tag}: `ncu --set full --clock-control none` (one launch per kernel; layer kernels 4096 signals per launch, k_dc 2368, k_classic_p 65536)\n")
+for name, (_, r, I, units) in best.items():
     out.write(f"\n## {name}\n\n| metric | value | unit |\n|---|---|---|\n")
     for w in want:
         if w in I:

@@ -25,7 +25,7 @@ def built():
 
 def test_library_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "admmnet_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|double|const char\*)\s+(\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(built.EXPORTS), declared ^ set(built.EXPORTS)
     L = built.lib()
     for name in declared:
