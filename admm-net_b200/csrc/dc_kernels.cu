@@ -134,18 +134,16 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
     int* kcol = kflag + 128;                                  // [128] compact index -> column
     int* cpos = kcol + 128;                                   // [128] rotation records of the serial scan
     int* blkof = cpos + 128;                                  // [128] block of index i at this level
-    int* lpos = blkof + 128;                                  // [128] compact index -> position in the child-ordered list
-    int* lcol = lpos + 128;                                   // [128] list position -> column (child 1's poles first)
-    float* lsd = reinterpret_cast<float*>(lcol + 128);        // [128] list position -> pole
-    float* lzh = lsd + 128;                                   // [128] list position -> Gu-Eisenstat z
-    float* rho_r = reinterpret_cast<float*>(lzh + 128);       // [64] per block: signed off-diagonal (0: nothing to merge)
+    float* csd = reinterpret_cast<float*>(blkof + 128);       // [128] column -> its pole (1e30 for a deflated column)
+    float* czh = csd + 128;                                   // [128] column -> its Gu-Eisenstat z (0 for a deflated column)
+    float* rho_r = czh + 256;                                 // [64] per block: signed off-diagonal (0: nothing to merge)
     int* kcnt = reinterpret_cast<int*>(rho_r + 64);           // [64] per block: non-deflated count
     int* serial = kcnt + 64;                                  // [64] per block: close poles found -> serial scan
     int* tb_lo = serial + 64;                                 // [64] block geometry of the level
     int* tb_p = tb_lo + 64;
     int* tb_hi = tb_p + 64;
-    int* kcnt1 = tb_hi + 64;                                  // [64] per block: kept poles that belong to the first child
-    int* toff = kcnt1 + 64;                                   // [65] first GEMM tile of block rb (exclusive scan)
+    int* mixed = tb_hi + 64;                                  // [64] per block: a Givens rotation mixed columns of the two children
+    int* toff = mixed + 64;                                   // [65] first GEMM tile of block rb (exclusive scan)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int sig = blockIdx.x;
     if (a.skip && a.skip[sig]) return;
@@ -182,7 +180,12 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             reinterpret_cast<float4*>(Qb)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        if (tid < a.ntear) es[a.tear_pos[tid] - 1] = (float)a.beta_in[(size_t)sig * a.tear_stride + tid];
+        if (tid < a.ntear) {
+            int tp = 1;                                          // (static indexing: a dynamically indexed kernel
+#pragma unroll                                                   //  parameter array would be copied to local memory)
+            for (int q = 0; q < 7; ++q) if (q == tid) tp = a.tear_pos[q];
+            es[tp - 1] = (float)a.beta_in[(size_t)sig * a.tear_stride + tid];
+        }
     }
     int nl = 0;
     while ((1 << nl) < d) ++nl;
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 lo_ = (tid * d) / nb; hi_ = ((tid + 1) * d) / nb; p_ = ((2 * tid + 1) * d) / (2 * nb);
                 if (lo_ < p_ && p_ < hi_) rr = es[p_ - 1];
             }
-            tb_lo[tid] = lo_; tb_p[tid] = p_; tb_hi[tid] = hi_; rho_r[tid] = rr; kcnt[tid] = 0; serial[tid] = 0;
+            tb_lo[tid] = lo_; tb_p[tid] = p_; tb_hi[tid] = hi_; rho_r[tid] = rr; kcnt[tid] = 0; serial[tid] = 0; mixed[tid] = 0;
         }
         int r = 0;
         if (tid < d) { r = dc_blk(tid, nb, d); blkof[tid] = r; }
@@ -229,17 +232,14 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             }
             if (j < hi) { dmax = fmaxf(dmax, fabsf(lamv[j])); zmax = fmaxf(zmax, fabsf(zloc[j])); }
             tol = 8.f * 5.9604645e-8f * fmaxf(fmaxf(dmax, dmax1), fmaxf(zmax, zmax1));
-            // rank among the poles of the block, compact index among the kept ones, and among the kept ones of the
-            // first child (columns < p)
-            int rank = lo, ci = 0, c1 = 0;
+            // rank among the poles of the block and compact index among the kept ones
+            int rank = lo, ci = 0;
 #pragma unroll 4
             for (int jj = lo; jj < hi; ++jj) {
                 const float dj = lamv[jj];
                 const int before = (dj < di || (dj == di && jj < tid)) ? 1 : 0;
-                const int kb = (before && rho * fabsf(zloc[jj]) > tol) ? 1 : 0;
                 rank += before;
-                ci += kb;
-                c1 += (kb && jj < p) ? 1 : 0;
+                ci += (before && rho * fabsf(zloc[jj]) > tol) ? 1 : 0;
             }
             const int keep = (rho * fabsf(zi) > tol) ? 1 : 0;
             sd[rank] = di;
@@ -251,9 +251,8 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 ksz[lo + ci] = zi;
                 ksz2[lo + ci] = zi * zi;
                 kcol[lo + ci] = tid;
-                lpos[lo + ci] = tid < p ? c1 : -(ci - c1) - 1;      // second child: -(index in its own list) - 1
             }
-            if (rank == hi - 1) { kcnt[r] = ci + keep; kcnt1[r] = c1 + ((keep && tid < p) ? 1 : 0); }
+            if (rank == hi - 1) kcnt[r] = ci + keep;
         }
         __syncthreads();
         DC_MARK(lev, 1)
@@ -318,22 +317,17 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 }
                 // rebuild the compact arrays of the scanned blocks
                 if (live && serial[r] > 0) {
-                    int ci = 0, c1 = 0;
-                    for (int t = lo; t < tid; ++t) { ci += kflag[t]; c1 += (kflag[t] && perm[t] < p) ? 1 : 0; }
-                    const int col = perm[tid];
+                    int ci = 0;
+                    for (int t = lo; t < tid; ++t) ci += kflag[t];
                     if (kflag[tid]) {
                         ksd[lo + ci] = sd[tid];
                         ksz[lo + ci] = sz[tid];
                         ksz2[lo + ci] = sz[tid] * sz[tid];
-                        kcol[lo + ci] = col;
-                        lpos[lo + ci] = col < p ? c1 : -(ci - c1) - 1;
+                        kcol[lo + ci] = perm[tid];
                     }
-                    // a Givens rotation may mix columns of the two children: the block's GEMM then takes the full
-                    // list for every coordinate group (kcnt1 < 0)
-                    if (tid == hi - 1) {
-                        kcnt[r] = ci + kflag[tid];
-                        kcnt1[r] = serial[r] > 1 ? -1 : c1 + ((kflag[tid] && col < p) ? 1 : 0);
-                    }
+                    // a Givens rotation may mix columns of the two children: the block's GEMM then takes every column
+                    // of the block for every coordinate group
+                    if (tid == hi - 1) { kcnt[r] = ci + kflag[tid]; mixed[r] = serial[r] > 1 ? 1 : 0; }
                 }
                 __syncthreads();
             }
@@ -497,16 +491,16 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                     for (; i < k; ++i) { const float w0 = pz[i] * dc_rcp((pd[i] - o) - x); s0 = fmaf(w0, w0, s0); }
                     nus[tid] = rsqrtf((s0 + s1) + (s2 + s3));
                     lamv[kcol[tid]] = o + x;
-                    // child-ordered copies for the GEMM: the first child's poles, then the second child's
-                    const int lp = lpos[tid];
-                    const int k1 = kcnt1[r];
-                    const int pos = k1 < 0 ? tid : lo + (lp >= 0 ? lp : k1 + (-lp - 1));
-                    lsd[pos] = pd[u];
-                    lzh[pos] = pz[u];
-                    lcol[pos] = kcol[tid];
+                    // pole and z by COLUMN for the GEMM, which walks the columns of a child in their natural order
+                    csd[kcol[tid]] = pd[u];
+                    czh[kcol[tid]] = pz[u];
                 }
                 const int kf = kflag[tid];
-                if (!kf) lamv[perm[tid]] = sd[tid];                  // deflated: (possibly rotated) pole, own column
+                if (!kf) {                                           // deflated: (possibly rotated) pole, own column;
+                    lamv[perm[tid]] = sd[tid];                       // its row of W is zero (1e30: no 0 * inf)
+                    csd[perm[tid]] = 1e30f;
+                    czh[perm[tid]] = 0.f;
+                }
                 zloc[perm[tid]] = kf ? 1.f : 0.f;
             } else {
                 zloc[tid] = 0.f;
@@ -517,7 +511,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
         // ---- P9: Q <- Q W.  Output row = column kcol[j] of the block, coordinates [lo, hi).
         float* out = top ? Zg : Qb;
         if (top) {
-            // materialise W in Qb: row i = pole, column j = root: zhat_i nu_j / (d_i - l_j), pitch ldz (k <= d <= ldz)
+            // materialise W in Qb: row = column of Q (its pole), column j = root: zhat nu_j / (d - l_j), pitch ldz
             if (rho_r[0] != 0.f) {
                 const int k = kcnt[0], kp = (k + 3) & ~3;
                 float oj[4], mj[4], nj[4];
@@ -529,12 +523,12 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                     mj[x] = okj ? mus[j] : 1.f;
                     nj[x] = okj ? nus[j] : 0.f;
                 }
-                for (int l = wid; l < k; l += DCK_NT / 32) {
-                    const float zi = lzh[l], di = lsd[l];
+                for (int c = wid; c < d; c += DCK_NT / 32) {         // row = COLUMN c of Q (zero for a deflated one)
+                    const float zi = czh[c], di = csd[c];
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
                         const int j = lane + 32 * x;
-                        if (j < kp) Qb[l * ldz + j] = j < k ? zi * nj[x] * dc_rcp((di - oj[x]) - mj[x]) : 0.f;
+                        if (j < kp) Qb[c * ldz + j] = j < k ? zi * nj[x] * dc_rcp((di - oj[x]) - mj[x]) : 0.f;
                     }
                 }
             }
@@ -552,22 +546,30 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 const int c0 = blo & ~3;
                 const int nct = (bhi - c0 + 3) >> 2;
                 const int tile = t - toff[rb];
-                const int jt = tile / nct, ct = tile - jt * nct;
+                // side-major order - groups inside the first child, inside the second, then the (at most one per root
+                // group) that straddles the split: the tiles of a warp run the same number of iterations
+                const int bp = tb_p[rb], mx = mixed[rb];
+                const int njt = (k + 3) >> 2;
+                const int n1 = mx ? 0 : (bp - c0) >> 2, ns = mx ? nct : (((bp - c0) & 3) ? 1 : 0), n2 = nct - n1 - ns;
+                int jt, ct;
+                if (tile < n1 * njt) { jt = tile / n1; ct = tile - jt * n1; }
+                else if (tile < (n1 + n2) * njt) { const int t2 = tile - n1 * njt; jt = t2 / n2; ct = n1 + ns + (t2 - jt * n2); }
+                else { const int t3 = tile - (n1 + n2) * njt; jt = t3 / ns; ct = n1 + (t3 - jt * ns); }
                 const int j0 = 4 * jt, cc = c0 + 4 * ct;
                 float acc[4][4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
                     for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-                // a column of the first child is zero on the second child's coordinates and vice versa: only the list
-                // range of the tile's side contributes (a coordinate group that straddles the split takes both)
-                const int bp = tb_p[rb], k1 = kcnt1[rb];
-                const int ibeg = (k1 >= 0 && cc >= bp) ? k1 : 0, iend = (k1 >= 0 && cc + 3 < bp) ? k1 : k;
+                // a column of the first child is zero on the second child's coordinates and vice versa: only the columns
+                // of the tile's own child contribute (a coordinate group that straddles the split takes both); the
+                // columns are walked in natural order - plain strided addresses, four iterations of loads in flight
+                const int cbeg = (!mx && cc >= bp) ? bp : blo, cend = (!mx && cc + 3 < bp) ? bp : bhi;
                 if (top) {
-#pragma unroll 2
-                    for (int i = ibeg; i < iend; ++i) {
-                        const float4 qv = *reinterpret_cast<const float4*>(Qa + lcol[i] * ldz + cc);
-                        const float4 wv = *reinterpret_cast<const float4*>(Qb + i * ldz + j0);
+#pragma unroll 4
+                    for (int c = cbeg; c < cend; ++c) {
+                        const float4 qv = *reinterpret_cast<const float4*>(Qa + c * ldz + cc);
+                        const float4 wv = *reinterpret_cast<const float4*>(Qb + c * ldz + j0);
                         acc[0][0] = fmaf(wv.x, qv.x, acc[0][0]); acc[0][1] = fmaf(wv.x, qv.y, acc[0][1]);
                         acc[0][2] = fmaf(wv.x, qv.z, acc[0][2]); acc[0][3] = fmaf(wv.x, qv.w, acc[0][3]);
                         acc[1][0] = fmaf(wv.y, qv.x, acc[1][0]); acc[1][1] = fmaf(wv.y, qv.y, acc[1][1]);
@@ -586,10 +588,10 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                         mj[x] = okj ? mus[blo + j0 + x] : 1.f;
                         nj[x] = okj ? nus[blo + j0 + x] : 0.f;
                     }
-#pragma unroll 2
-                    for (int i = ibeg; i < iend; ++i) {
-                        const float4 qv = *reinterpret_cast<const float4*>(Qa + lcol[blo + i] * ldz + cc);
-                        const float di = lsd[blo + i], zi = lzh[blo + i];
+#pragma unroll 4
+                    for (int c = cbeg; c < cend; ++c) {
+                        const float4 qv = *reinterpret_cast<const float4*>(Qa + c * ldz + cc);
+                        const float di = csd[c], zi = czh[c];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
                             const float w = zi * nj[x] * dc_rcp((di - oj[x]) - mj[x]);
