@@ -3,7 +3,7 @@
 // signal replaces the k_ql + k_rotf pair (one-thread-per-signal fp64 QL chain + 8.5k plane rotations per matrix).
 //
 //   T is torn at EVERY off-diagonal (Cuppen): leaves are 1 x 1 (l_i = d_i - |e_{i-1}| - |e_i|, Q = I), and a binary
-//   tree of ceil(log2 d) levels glues neighbouring blocks.  One merge of the blocks [lo,p) and [p,hi):
+//   tree of ceil(log2 d) levels glues neighbouring blocks (the first level, 2 x 2 problems, in closed form).  One merge of the blocks [lo,p) and [p,hi):
 //       diag(l) + rho z z^T,   rho = 2|e_{p-1}|,   z = (last row of Q1, sign(e_{p-1}) * first row of Q2) / sqrt(2)
 //     - poles sorted by rank, deflation as LAPACK's xLAED2 (rho |z_i| <= tol: pair kept; (nearly) equal poles: Givens
 //       rotation of the two columns - detected in parallel, carried out by a serial scan only when it occurs)
@@ -158,8 +158,10 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
         tlast = tnow;                                         \
     }
 
+    int nl = 0;
+    while ((1 << nl) < d) ++nl;
     if (a.nhyb == 0) {
-        // ---- leaves: every off-diagonal is a tear
+        // ---- leaves: every off-diagonal is a tear (leaf value d_i - |e_{i-1}| - |e_i|) ...
         if (tid < d) {
             const float di = a.dT[(size_t)tid * a.B + sig];
             const float e_own = tid < d - 1 ? a.eT[(size_t)tid * a.B + sig] : 0.f;
@@ -167,11 +169,34 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             lamv[tid] = di - fabsf(e_prev) - fabsf(e_own);
             es[tid] = e_own;
         }
-        for (int c = wid; c < d; c += DCK_NT / 32)
-            for (int x = lane; x < ldz; x += 32) {
-                Qa[c * ldz + x] = (c == x) ? 1.f : 0.f;
-                Qb[c * ldz + x] = 0.f;      // a column's coordinates outside its own block are read as zeros by every later merge
+        for (int idx = tid; idx < d * ldz / 4; idx += DCK_NT) {
+            reinterpret_cast<float4*>(Qa)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(Qb)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);   // a column's coordinates outside its own
+        }                                                                            // block are read as zeros by every merge
+        __syncthreads();
+        // ... and the first merge level in closed form: its blocks have one or two rows, and the 2 x 2 problem
+        //     [[l0 + |b|, b], [b, l1 + |b|]] is one Jacobi rotation (thread = block)
+        const int nb1 = 1 << (nl - 1);
+        if (tid < nb1) {
+            const int lo = (tid * d) / nb1, hi = ((tid + 1) * d) / nb1;
+            if (hi - lo == 2) {
+                const float b = es[lo];
+                float cs = 1.f, sn = 0.f;
+                if (b != 0.f) {
+                    const float aa = lamv[lo] + fabsf(b), cc = lamv[lo + 1] + fabsf(b);
+                    const float theta = (cc - aa) / (2.f * b);
+                    const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
+                    cs = 1.f / sqrtf(fmaf(t, t, 1.f));
+                    sn = t * cs;
+                    lamv[lo] = aa - t * b;
+                    lamv[lo + 1] = cc + t * b;
+                }
+                Qa[lo * ldz + lo] = cs;          Qa[lo * ldz + lo + 1] = -sn;       // row = eigenvector, column = coordinate
+                Qa[(lo + 1) * ldz + lo] = sn;    Qa[(lo + 1) * ldz + lo + 1] = cs;
+            } else if (hi - lo == 1) {
+                Qa[lo * ldz + lo] = 1.f;
             }
+        }
     } else {
         // ---- blocks solved by the QL pair: eigenvalues, block-diagonal Q^T and the torn off-diagonals from global memory
         if (tid < d) { lamv[tid] = a.lam[(size_t)sig * d + tid]; es[tid] = 0.f; }
@@ -187,12 +212,10 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             es[tp - 1] = (float)a.beta_in[(size_t)sig * a.tear_stride + tid];
         }
     }
-    int nl = 0;
-    while ((1 << nl) < d) ++nl;
     bool bad = false;
     __syncthreads();
 
-    for (int lev = a.nhyb ? nl - a.nhyb + 1 : 1; lev <= nl; ++lev) {
+    for (int lev = a.nhyb ? nl - a.nhyb + 1 : 2; lev <= nl; ++lev) {
         const int nb = 1 << (nl - lev);
         const bool top = lev == nl;
         // ---- P0: block tables of the level

@@ -4,7 +4,9 @@ D + rho z z^T solved through its secular equation in coordinates shifted to the 
 re-derivation of z from the computed roots (orthogonal eigenvectors for any pole spacing), deflation of negligible z
 and of (nearly) equal poles as LAPACK's xLAED2.  The emulation follows the kernel step by step (same formulas, same
 tolerances) so that the algorithm's accuracy can be studied without a GPU; tests/test_host_cpu.py runs it on random,
-clustered, graded and degenerate tridiagonals.
+clustered, graded and degenerate tridiagonals.  (Two implementation shortcuts of the kernel are not mirrored because
+they do not change the mathematics: its first merge level - blocks of one or two rows - is a closed-form 2 x 2 Jacobi
+rotation, and its merge products skip the structural zeros of the other child's columns.)
 """
 import numpy as np
 
