@@ -248,6 +248,12 @@ inline int dc_levels(int d, int B) {
 // Hybrid plan for many-chunk batches (ADMMNET_HYB = levels, default below): k_ql + k_rotf solve the 2^L blocks of the torn
 // tridiagonal (half / quarter length sweeps: the latency-bound QL chain and the rotation count shrink accordingly) and
 // k_dc runs only the top L merge levels.
+// ADMMNET_MIX=1: in a many-chunk forward the odd chunk lanes take k_dc and the even ones the QL pair, so that every
+// latency-bound k_ql runs beside a throughput-bound lane (experiment; see DESIGN.md §5 for the measurement).
+inline bool mix_lanes() {
+    static const bool on = getenv("ADMMNET_MIX") && atoi(getenv("ADMMNET_MIX")) != 0;
+    return on;
+}
 inline int hyb_levels(int d) {
     static const int env = getenv("ADMMNET_HYB") ? atoi(getenv("ADMMNET_HYB")) : 0;
     int L = env < 0 ? 0 : (env > 2 ? 2 : env);
@@ -615,7 +621,7 @@ static int layer_chunk_impl(const void* y, const void* b, const float* sigma, in
     CK(cudaGetLastError());
     if (int e = launch_head2(w, Bc, d, st, skip)) return e;
     return launch_eig_tail(w, Bc, n, d, rcap, h.Pk, 1, nullptr, nullptr, w.status, st, qst, ev_in, ev_out, skip,
-                           /*lone=*/B <= chunk);
+                           /*lone=*/B <= chunk || (mix_lanes() && (slot & 1)));
 }
 
 extern "C" int admmnet_reset_status(void* ws, size_t ws_bytes, int B, int chunk, int n, int K, int rcap, void* stream) {

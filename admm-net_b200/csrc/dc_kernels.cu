@@ -295,49 +295,50 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             }
             if (__syncthreads_or(close)) {
                 if (live && tid == lo && serial[r]) {
+                    // (kflag already marks the negligible z; the previous kept pole and its z ride in registers, so an
+                    //  iteration is two independent loads and, only when a rotation fires, a short dependent update)
                     int prev = -1, nrot = 0;
+                    float zp = 0.f, dp = 0.f;
+#pragma unroll 4
                     for (int t = lo; t < hi; ++t) {
-                        if (!(rho * fabsf(sz[t]) > tol)) { kflag[t] = 0; continue; }
-                        kflag[t] = 1;
+                        float zt = sz[t], dt = sd[t];
+                        if (!kflag[t]) continue;
                         if (prev >= 0) {
-                            const float s_ = sz[prev], c_ = sz[t];
-                            const float tau = sqrtf(c_ * c_ + s_ * s_);
-                            const float tt = sd[t] - sd[prev];
-                            const float c = c_ / tau, s = -s_ / tau;
-                            if (fabsf(tt * c * s) <= tol) {
+                            const float tau2 = fmaf(zt, zt, zp * zp);
+                            if (fabsf((dt - dp) * zt * zp) <= tol * tau2) {   // |tt c s| <= tol with c, s = zt, -zp / tau
+                                const float rt = rsqrtf(tau2);
+                                const float c = zt * rt, s = -zp * rt;
                                 // columns perm[prev], perm[t]: z[prev] -> 0, z[t] -> tau  (record; applied below)
                                 // the record reuses the compact arrays of this block, which are rebuilt right after
                                 ksd[lo + nrot] = c; ksz[lo + nrot] = s;
                                 kcol[lo + nrot] = perm[prev]; cpos[lo + nrot] = perm[t];
                                 ++nrot;
-                                const float dp = sd[prev], dt = sd[t];
-                                sd[prev] = dp * c * c + dt * s * s;
-                                sd[t] = dp * s * s + dt * c * c;
-                                sz[t] = tau; sz[prev] = 0.f;
-                                kflag[prev] = 0;
+                                const float dpn = dp * c * c + dt * s * s;
+                                dt = dp * s * s + dt * c * c;
+                                zt = tau2 * rt;
+                                sd[prev] = dpn; sz[prev] = 0.f; kflag[prev] = 0;
+                                sd[t] = dt; sz[t] = zt;
                             }
                         }
-                        prev = t;
+                        prev = t; zp = zt; dp = dt;
                     }
                     serial[r] = nrot + 1;
                 }
                 __syncthreads();
-                // apply the recorded rotations block by block (all threads walk the same lists)
-                for (int rb = 0; rb < nb; ++rb) {
-                    const int nrot = serial[rb] - 1;
-                    if (nrot <= 0) continue;
-                    const int blo = tb_lo[rb], bhi = tb_hi[rb];
+                // apply the recorded rotations: a rotation mixes two columns coordinate by coordinate, so the thread
+                // of coordinate x runs through its block's whole list on its own (no barrier between rotations)
+                if (tid < d) {
+                    const int rb = blkof[tid], nrot = serial[rb] - 1;
+                    const int blo = tb_lo[rb];
                     for (int q = 0; q < nrot; ++q) {
                         const float c = ksd[blo + q], s = ksz[blo + q];
                         const int cp = kcol[blo + q], ct = cpos[blo + q];
-                        for (int x = blo + tid; x < bhi; x += DCK_NT) {
-                            const float qp = Qa[cp * ldz + x], qt = Qa[ct * ldz + x];
-                            Qa[cp * ldz + x] = c * qp + s * qt;
-                            Qa[ct * ldz + x] = -s * qp + c * qt;
-                        }
-                        __syncthreads();
+                        const float qp = Qa[cp * ldz + tid], qt = Qa[ct * ldz + tid];
+                        Qa[cp * ldz + tid] = c * qp + s * qt;
+                        Qa[ct * ldz + tid] = -s * qp + c * qt;
                     }
                 }
+                __syncthreads();
                 // rebuild the compact arrays of the scanned blocks
                 if (live && serial[r] > 0) {
                     int ci = 0;
