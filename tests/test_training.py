@@ -125,7 +125,7 @@ def test_training_gradients_match_reference_gpu():
     loss.backward()
     assert np.abs(phi.detach().cpu().numpy() - z["phi"]).max() < 1e-4 * np.abs(z["phi"]).max()
     assert abs(float(loss.detach()) - float(z["loss"])) < 1e-4 * float(z["loss"])
-    worst = _compare_grads(model, grads, 5e-3)
+    worst = _compare_grads(model, grads, 1e-3)          # measured on B200: 2.6e-4
     print("worst relative gradient error", worst)
 
 
