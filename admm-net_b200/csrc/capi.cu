@@ -373,7 +373,16 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
         CK(ensure_smem(k_rot, (int)sm));
         prof::Scope pscope(prof::ROT, st);
         static const bool fused = !(getenv("ADMMNET_ROTF") && atoi(getenv("ADMMNET_ROTF")) == 0);
-        if (fused) {      // same shared-memory size: ring of 4 x 256 entries instead of 2 x 512
+        // ADMMNET_ROTP=1: the coordinates of a signal split over two one-warp CTAs (k_rotf_p<2, 2>: 7 instead of 4
+        // resident warps per SM, half the packed operations per rotation and warp).  Parity-identical, measured 8 %
+        // slower (k_rot 276 -> 297 ms per 131072 signals x 8 layers: the per-rotation overhead - parameter loads, ring
+        // indexing - is paid by both warps), so it stays opt-in.
+        static const bool panels = getenv("ADMMNET_ROTP") && atoi(getenv("ADMMNET_ROTP")) != 0;
+        if (fused && panels) {
+            const size_t smp = (size_t)2 * ROT_STAGE * sizeof(float2) + (size_t)d * (2 * ((d + 3) / 4)) * sizeof(float);
+            CK(ensure_smem(k_rotf_p<2, 2>, (int)smp));
+            k_rotf_p<2, 2><<<2 * B, ROT_THREADS, smp, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
+        } else if (fused) {      // same shared-memory size: ring of 4 x 256 entries instead of 2 x 512
             CK(ensure_smem(k_rotf, (int)sm));
             k_rotf<<<B, ROT_THREADS, sm, st>>>(w.rot, rcap, w.nrot, d, w.Zr, skip);
         } else

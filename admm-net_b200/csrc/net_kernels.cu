@@ -1090,6 +1090,226 @@ k_rotf(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, i
     for (int idx = lane; idx < d * ldr / 4; idx += 32) outz[idx] = z4[idx];
 }
 
+// ---- k_rotf_p: k_rotf with the coordinates of a signal split over SPLIT one-warp CTAs (VW coordinates per lane).  A plane
+// rotation mixes two rows of Z^T coordinate by coordinate, so panels of coordinates are independent; a panel needs
+// 1/SPLIT of the shared memory (7 CTAs per SM instead of 4 at SPLIT = 2) and half the packed operations per rotation,
+// which matters because a lone warp on an SM sub-partition issues at most every other cycle: more resident warps, each
+// with fewer instructions per rotation.  Every CTA of a signal streams the whole rotation list (L2 hits).
+template <int VW> struct RotVec;
+template <> struct RotVec<4> { using type = float4; };
+template <> struct RotVec<2> { using type = float2; };
+__device__ __forceinline__ void rotv(float4& out, float4& cy, const float4 zi, const float2 e) { rot4(out, cy, zi, e); }
+__device__ __forceinline__ void rotv(float2& out, float2& cy, const float2 zi, const float2 e) {
+    const f32x2 c2 = bc2(e.x), s2 = bc2(e.y), ns2 = bc2(-e.y);
+    const f32x2 z = pk2(zi.x, zi.y), f = pk2(cy.x, cy.y);
+    out = upk2(fma2(s2, z, mul2(c2, f)));
+    cy = upk2(fma2(c2, z, mul2(ns2, f)));
+}
+template <int VW, int SPLIT>
+__global__ void __launch_bounds__(ROT_THREADS)
+k_rotf_p(const float2* __restrict__ rot, int rcap, const int* __restrict__ nrot, int d, float* __restrict__ Zt,
+         const int* __restrict__ skip) {
+    using VT = typename RotVec<VW>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* ring = reinterpret_cast<float2*>(smem_raw);                   // [4][ROTF_STG]
+    float* z = reinterpret_cast<float*>(ring + 4 * ROTF_STG);             // [d][ldp]: this CTA's panel of coordinates
+    const int ldr = 4 * ((d + 3) / 4);
+    const int ldp = ldr / SPLIT;
+    const int lane = threadIdx.x;
+    const int sig = blockIdx.x / SPLIT, part = blockIdx.x % SPLIT;
+    if (skip && skip[sig]) return;
+    const float2* src = rot + (size_t)sig * rcap;
+    const int total = nrot[sig];
+    for (int idx = lane; idx < d * ldp; idx += 32) z[idx] = 0.f;
+    __syncwarp();
+    for (int r = lane; r < d; r += 32) {
+        const int x = r - part * ldp;
+        if (x >= 0 && x < ldp) z[r * ldp + x] = 1.f;
+    }
+    const int nstages = (total + ROTF_STG - 1) / ROTF_STG;
+    auto issue = [&](int k) {                                             // stage k -> ring slot k & 3 (one group)
+        if (k < nstages) {
+            const float2* g = src + (size_t)k * ROTF_STG;
+            float2* sdst = ring + (k & 3) * ROTF_STG;
+#pragma unroll
+            for (int q = lane; q < ROTF_STG / 2; q += 32) cp_async16(sdst + 2 * q, g + 2 * q);
+        }
+        cp_async_commit();
+    };
+    issue(0); issue(1); issue(2);
+    cp_async_wait<1>();                                                   // stages 0 and 1 have landed
+    __syncwarp();
+    int cur = 0;
+    const bool act = VW * lane < ldp;
+    VT* zq = reinterpret_cast<VT*>(z) + (act ? lane : 0);                // column c at zq[c * lq]
+    const int lq = ldp / VW;
+#define RING(e) ring[(e) & (4 * ROTF_STG - 1)]
+    int q = 0;
+    while (q < total) {
+        while ((q / ROTF_STG) > cur) {                                    // entered a new stage: keep two landed ahead
+            ++cur;
+            __syncwarp();                                                 // every lane is done with stage cur-1
+            issue(cur + 2);
+            cp_async_wait<1>();
+            __syncwarp();
+        }
+        const float2 hA = RING(q);
+        const int mA = __float_as_int(hA.x);
+        if (mA < 0) break;
+        const int cntA = __float_as_int(hA.y);
+        const int qa = q + 1;
+        const int qB = qa + cntA;
+        bool pair = false;
+        int mB = 0, cntB = 0;
+        if (cntA > 0 && qB < total) {
+            const float2 hB = RING(qB);
+            mB = __float_as_int(hB.x);
+            cntB = __float_as_int(hB.y);
+            if (mB >= 0 && cntB > 0) {
+                const int top = max(mA, mB) - 1, end = min(mA - cntA, mB - cntB - 1);
+                pair = 20 * (top - end + 1) <= 17 * (cntA + cntB);
+            }
+        }
+        if (pair) {
+            const int qb = qB + 1;
+            const int lA = mA - cntA, lB = mB - cntB;
+            const int itop = max(mA, mB) - 1, iend = min(lA, lB - 1);
+            VT cA = zq[(itop + 1) * lq], cB;
+            {   // first step: A only, its output is B's first carry
+                const VT zi = zq[itop * lq];
+                if (itop <= mA - 1 && itop >= lA) {
+                    rotv(cB, cA, zi, RING(qa + mA - 1 - itop));
+                } else { cB = cA; cA = zi; }
+            }
+            int i = itop - 1;
+            // core: both sweeps active, two steps per trip, loads first
+            const int core_lo = max(lA, lB - 1);
+            const int core_hi = min(mA - 1, mB - 2);
+            // flagged steps above the core
+            for (; i >= iend && i > core_hi; --i) {
+                const VT zi = i >= 0 ? zq[i * lq] : VT{};
+                VT oA, oB;
+                if (i <= mA - 1 && i >= lA) rotv(oA, cA, zi, RING(qa + mA - 1 - i)); else { oA = cA; cA = zi; }
+                if (i + 1 <= mB - 1 && i + 1 >= lB) rotv(oB, cB, oA, RING(qb + mB - 2 - i)); else { oB = cB; cB = oA; }
+                if (act) zq[(i + 2) * lq] = oB;
+            }
+            // (requesting the next trip's operands ahead of the FMA chain was measured slower: 376 -> 426 ms)
+            {
+                // fast form of the core loop: when neither sweep's parameters wrap around the ring inside this pair
+                // (4 pairs out of 5) plain pointers replace the masked index arithmetic (5 instead of 24 integer
+                // instructions per trip, and a lone warp pays two cycles for every instruction it issues)
+                const int ntr = i - 1 >= core_lo ? (i - core_lo + 1) / 2 : 0;
+                const int ia = (qa + mA - 1 - i) & (4 * ROTF_STG - 1), ib = (qb + mB - 2 - i) & (4 * ROTF_STG - 1);
+                if (ntr > 0 && ia + 2 * ntr <= 4 * ROTF_STG && ib + 2 * ntr <= 4 * ROTF_STG) {
+                    const float2* pa = ring + ia;
+                    const float2* pb = ring + ib;
+                    VT* zp = zq + i * lq;
+                    // two register sets: the loads of trip t+1 are issued before the FMA chain of trip t (pure
+                    // reordering, no extra instructions; a load past the last trip reads valid, unused shared memory)
+#define ROTF_LD(S, K)                                                                          \
+    const float2 ea0##S = pa[2 * (K)], ea1##S = pa[2 * (K) + 1], eb0##S = pb[2 * (K)], eb1##S = pb[2 * (K) + 1]; \
+    const VT z0##S = zp[-2 * (K) * lq], z1##S = zp[-(2 * (K) + 1) * lq];
+#define ROTF_DO(S, K)                                                                          \
+    {                                                                                          \
+        VT oA0, oB0, oA1, oB1;                                                             \
+        rotv(oA0, cA, z0##S, ea0##S);                                                          \
+        rotv(oB0, cB, oA0, eb0##S);                                                            \
+        rotv(oA1, cA, z1##S, ea1##S);                                                          \
+        rotv(oB1, cB, oA1, eb1##S);                                                            \
+        if (act) { zp[(2 - 2 * (K)) * lq] = oB0; zp[(1 - 2 * (K)) * lq] = oB1; }               \
+    }
+                    int tr = 0;
+                    for (; tr + 4 <= ntr; tr += 4) {
+                        ROTF_LD(X, 0)
+                        ROTF_LD(Y, 1)
+                        ROTF_LD(V, 2)
+                        ROTF_LD(W, 3)
+                        ROTF_DO(X, 0)
+                        ROTF_DO(Y, 1)
+                        ROTF_DO(V, 2)
+                        ROTF_DO(W, 3)
+                        pa += 8; pb += 8; zp -= 8 * lq;
+                    }
+                    if (tr + 2 <= ntr) {
+                        ROTF_LD(X, 0)
+                        ROTF_LD(Y, 1)
+                        ROTF_DO(X, 0)
+                        ROTF_DO(Y, 1)
+                        pa += 4; pb += 4; zp -= 4 * lq;
+                        tr += 2;
+                    }
+                    if (tr < ntr) {
+                        ROTF_LD(X, 0)
+                        ROTF_DO(X, 0)
+                    }
+#undef ROTF_LD
+#undef ROTF_DO
+                    i -= 2 * ntr;
+                }
+            }
+            for (; i - 1 >= core_lo; i -= 2) {
+                const float2 ea0 = RING(qa + mA - 1 - i), ea1 = RING(qa + mA - i);
+                const float2 eb0 = RING(qb + mB - 2 - i), eb1 = RING(qb + mB - 1 - i);
+                const VT z0 = zq[i * lq], z1 = zq[(i - 1) * lq];
+                VT oA0, oB0, oA1, oB1;
+                rotv(oA0, cA, z0, ea0);
+                rotv(oB0, cB, oA0, eb0);
+                rotv(oA1, cA, z1, ea1);
+                rotv(oB1, cB, oA1, eb1);
+                if (act) { zq[(i + 2) * lq] = oB0; zq[(i + 1) * lq] = oB1; }
+            }
+            // flagged steps below (and the odd core step)
+            for (; i >= iend; --i) {
+                const VT zi = i >= 0 ? zq[i * lq] : VT{};
+                VT oA, oB;
+                if (i <= mA - 1 && i >= lA) rotv(oA, cA, zi, RING(qa + mA - 1 - i)); else { oA = cA; cA = zi; }
+                if (i + 1 <= mB - 1 && i + 1 >= lB) rotv(oB, cB, oA, RING(qb + mB - 2 - i)); else { oB = cB; cB = oA; }
+                if (act) zq[(i + 2) * lq] = oB;
+            }
+            if (act) {
+                zq[(iend + 1) * lq] = cB;
+                if (iend >= 0) zq[iend * lq] = cA;
+            }
+            q = qb + cntB;
+        } else {
+            // single sweep (as k_rot): batches of 4 rotations, loads first
+            int col = mA;
+            VT carry = zq[col * lq];
+            int t = 0;
+            for (; t + 4 <= cntA; t += 4) {
+                const float2 e0 = RING(qa + t), e1 = RING(qa + t + 1), e2 = RING(qa + t + 2), e3 = RING(qa + t + 3);
+                VT* zp = zq + (col - 1 - t) * lq;
+                const VT z0 = zp[0], z1 = zp[-lq], z2 = zp[-2 * lq], z3 = zp[-3 * lq];
+                VT o0, o1, o2, o3;
+                rotv(o0, carry, z0, e0);
+                rotv(o1, carry, z1, e1);
+                rotv(o2, carry, z2, e2);
+                rotv(o3, carry, z3, e3);
+                if (act) { zp[lq] = o0; zp[0] = o1; zp[-lq] = o2; zp[-2 * lq] = o3; }
+            }
+            for (; t < cntA; ++t) {
+                const float2 e = RING(qa + t);
+                VT* zp = zq + (col - 1 - t) * lq;
+                const VT zi = zp[0];
+                VT o;
+                rotv(o, carry, zi, e);
+                if (act) zp[lq] = o;
+            }
+            if (act) zq[(col - cntA) * lq] = carry;
+            q = qB;
+        }
+    }
+#undef RING
+    __syncwarp();
+    // global Z^T keeps the padded row pitch ldr (16-byte aligned rows: TMA box source for k_tail_tc)
+    float* outz = Zt + (size_t)sig * d * ldr + part * ldp;
+    const VT* zv = reinterpret_cast<const VT*>(z);
+    for (int idx = lane; idx < d * lq; idx += 32) {
+        const int row = idx / lq, v = idx - row * lq;
+        *reinterpret_cast<VT*>(outz + (size_t)row * ldr + v * VW) = zv[idx];
+    }
+}
+
 // =====================================================================================
 // k_merge: one level of the divide & conquer merge tree.  Every range [a,b) of the level is the union of two
 // already-solved blocks torn at row p; eigenpairs of diag(D) + rho z z^T (z = Q^T v, poles D = block eigenvalues

@@ -633,7 +633,7 @@ def test_admmnet_full_module_matches_reference_golden(pkg):
 
 @pytest.mark.parametrize("switch", ["ADMMNET_ARROW", "ADMMNET_ROTF", "ADMMNET_TAILTC", "ADMMNET_LANES", "ADMMNET_TRD=1",
                                     "ADMMNET_DCK", "ADMMNET_DCK=0,ADMMNET_DC=2", "ADMMNET_DCK=0,ADMMNET_HYB=1",
-                                    "ADMMNET_DCK=0,ADMMNET_HYB=2"])
+                                    "ADMMNET_DCK=0,ADMMNET_HYB=2", "ADMMNET_DCK=0,ADMMNET_ROTP=1"])
 def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
     """Every fast path has a plain sibling behind an environment switch (read once per process, hence the
     subprocess): ADMMNET_ARROW=0 dense eigen-solver at layer 0 instead of the arrowhead shortcut, ADMMNET_ROTF=0
@@ -642,7 +642,8 @@ def test_alternative_kernel_paths_agree(pkg, tmp_path, switch):
     tridiagonalisation (opt-in) instead of the staged shared-memory one, ADMMNET_DCK=0 the QL pair instead of the fused
     divide & conquer kernel this single-chunk call takes by default (and with ADMMNET_DC=2 the legacy k_merge levels
     on top of it; with ADMMNET_HYB=1|2 the hybrid: QL pair on the 2 | 4 blocks of the torn tridiagonal, top merge
-    levels in k_dc).  Same inputs, same answer."""
+    levels in k_dc; with ADMMNET_ROTP=1 the panel-split rotation kernel, two one-warp CTAs per signal).
+    Same inputs, same answer."""
     import subprocess
     import sys
     z, sd = load_net_case("pert_k10")
