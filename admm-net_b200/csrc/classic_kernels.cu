@@ -174,6 +174,7 @@ k_classic_p(const float2* __restrict__ y, const float2* __restrict__ b, int B, i
         const float2* bs = ys + in_elems;
         double2* os = outb + (size_t)stage * in_elems;
         const int sl = SPW * wid + g;                         // signal within the tile
+        ADMM_ASSERT(sl < CLP_S && ns >= 1 && ns <= CLP_S && s0 + ns <= B && n <= GL * MAXE);
         const bool valid = sl < ns;
         double D[MAXE];
         double2 dyb[MAXE], phi[MAXE];

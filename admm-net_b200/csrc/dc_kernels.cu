@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             int tp = 1;                                          // (static indexing: a dynamically indexed kernel
 #pragma unroll                                                   //  parameter array would be copied to local memory)
             for (int q = 0; q < 7; ++q) if (q == tid) tp = a.tear_pos[q];
+            ADMM_ASSERT(tp >= 1 && tp < d);
             es[tp - 1] = (float)a.beta_in[(size_t)sig * a.tear_stride + tid];
         }
     }
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 ci += (before && rho * fabsf(zloc[jj]) > tol) ? 1 : 0;
             }
             const int keep = (rho * fabsf(zi) > tol) ? 1 : 0;
+            ADMM_ASSERT(rank >= lo && rank < hi && lo + ci < hi && hi <= d && hi - lo <= 128);
             sd[rank] = di;
             sz[rank] = zi;
             perm[rank] = tid;
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                                 const float c = zt * rt, s = -zp * rt;
                                 // columns perm[prev], perm[t]: z[prev] -> 0, z[t] -> tau  (record; applied below)
                                 // the record reuses the compact arrays of this block, which are rebuilt right after
+                                ADMM_ASSERT(lo + nrot < hi && perm[prev] >= lo && perm[prev] < hi && perm[t] >= lo && perm[t] < hi);
                                 ksd[lo + nrot] = c; ksz[lo + nrot] = s;
                                 kcol[lo + nrot] = perm[prev]; cpos[lo + nrot] = perm[t];
                                 ++nrot;
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                     for (int q = 0; q < nrot; ++q) {
                         const float c = ksd[blo + q], s = ksz[blo + q];
                         const int cp = kcol[blo + q], ct = cpos[blo + q];
+                        ADMM_ASSERT(cp >= 0 && cp < d && ct >= 0 && ct < d && cp != ct);
                         const float qp = Qa[cp * ldz + tid], qt = Qa[ct * ldz + tid];
                         Qa[cp * ldz + tid] = c * qp + s * qt;
                         Qa[ct * ldz + tid] = -s * qp + c * qt;
@@ -365,6 +369,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
             bool work = false;
             if (slot < d) {
                 const int r2 = blkof[slot];
+                ADMM_ASSERT(r2 >= 0 && r2 < nb && nb <= 64);
                 slo = tb_lo[r2];
                 srho = 2.f * fabsf(rho_r[r2]);
                 k = kcnt[r2];
@@ -516,6 +521,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                     nus[tid] = rsqrtf((s0 + s1) + (s2 + s3));
                     lamv[kcol[tid]] = o + x;
                     // pole and z by COLUMN for the GEMM, which walks the columns of a child in their natural order
+                    ADMM_ASSERT(kcol[tid] >= lo && kcol[tid] < hi && u < k && k <= hi - lo);
                     csd[kcol[tid]] = pd[u];
                     czh[kcol[tid]] = pz[u];
                 }
@@ -580,6 +586,8 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 else if (tile < (n1 + n2) * njt) { const int t2 = tile - n1 * njt; jt = t2 / n2; ct = n1 + ns + (t2 - jt * n2); }
                 else { const int t3 = tile - (n1 + n2) * njt; jt = t3 / ns; ct = n1 + (t3 - jt * ns); }
                 const int j0 = 4 * jt, cc = c0 + 4 * ct;
+                ADMM_ASSERT(rb < nb && tile >= 0 && tile < nct * njt && jt >= 0 && jt < njt && ct >= 0 && ct < nct);
+                ADMM_ASSERT(cc >= 0 && cc + 3 < ldz && j0 + 3 < ldz && k > 0 && k <= bhi - blo);
                 float acc[4][4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
@@ -589,6 +597,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
                 // of the tile's own child contribute (a coordinate group that straddles the split takes both); the
                 // columns are walked in natural order - plain strided addresses, four iterations of loads in flight
                 const int cbeg = (!mx && cc >= bp) ? bp : blo, cend = (!mx && cc + 3 < bp) ? bp : bhi;
+                ADMM_ASSERT(cbeg >= blo && cend <= bhi && cbeg <= cend && bhi <= d);
                 if (top) {
 #pragma unroll 4
                     for (int c = cbeg; c < cend; ++c) {
@@ -627,6 +636,7 @@ __global__ void __launch_bounds__(DCK_NT, 2) k_dc(DcArgs a) {
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     if (j0 + x >= k) continue;
+                    ADMM_ASSERT(kcol[blo + j0 + x] >= blo && kcol[blo + j0 + x] < bhi);
                     float* orow = out + (size_t)kcol[blo + j0 + x] * ldz;
 #pragma unroll
                     for (int y = 0; y < 4; ++y) {
