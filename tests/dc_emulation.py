@@ -4,9 +4,9 @@ D + rho z z^T solved through its secular equation in coordinates shifted to the 
 re-derivation of z from the computed roots (orthogonal eigenvectors for any pole spacing), deflation of negligible z
 and of (nearly) equal poles as LAPACK's xLAED2.  The emulation follows the kernel step by step (same formulas, same
 tolerances) so that the algorithm's accuracy can be studied without a GPU; tests/test_host_cpu.py runs it on random,
-clustered, graded and degenerate tridiagonals.  (Two implementation shortcuts of the kernel are not mirrored because
-they do not change the mathematics: its first merge level - blocks of one or two rows - is a closed-form 2 x 2 Jacobi
-rotation, and its merge products skip the structural zeros of the other child's columns.)
+clustered, graded and degenerate tridiagonals.  (The kernel's first merge level - blocks of one or two rows - is a closed-form 2 x 2 Jacobi
+rotation, mirrored by merge2_closed_form; that its merge products skip the structural zeros of the other child's
+columns does not change the mathematics and is not mirrored.)
 """
 import numpy as np
 
@@ -174,7 +174,23 @@ def merge(lam, Q, lo, p, hi, beta, stats=None):
     lam[cols] = newlam
 
 
-def dc_eigh(dT, eT, stats=None):
+def merge2_closed_form(lam, Q, lo, beta):
+    """The first merge level as csrc/dc_kernels.cu does it: a block of two leaves is the 2 x 2 problem
+    [[l0 + |b|, b], [b, l1 + |b|]], diagonalised by one Jacobi rotation (float32).  Columns of Q = eigenvectors."""
+    b = F(beta)
+    if b == 0:
+        return
+    aa, cc = F(lam[lo] + abs(b)), F(lam[lo + 1] + abs(b))
+    theta = F((cc - aa) / (F(2) * b))
+    t = F(np.copysign(F(1), theta) / (abs(theta) + np.sqrt(F(theta * theta + F(1)), dtype=F)))
+    cs = F(F(1) / np.sqrt(F(t * t + F(1)), dtype=F))
+    sn = F(t * cs)
+    lam[lo], lam[lo + 1] = F(aa - t * b), F(cc + t * b)
+    Q[lo, lo], Q[lo + 1, lo] = cs, -sn          # eigenvector of lam[lo]   (kernel: row lo of Q^T = (cs, -sn))
+    Q[lo, lo + 1], Q[lo + 1, lo + 1] = sn, cs   # eigenvector of lam[lo+1]
+
+
+def dc_eigh(dT, eT, stats=None, closed_form_level1=True):
     """Symmetric tridiagonal (diagonal dT [d], off-diagonal eT [d-1]) -> (lam [d] unsorted, Q [d][d]) in float32."""
     d = len(dT)
     dT, eT = np.asarray(dT, F), np.asarray(eT, F)
@@ -182,9 +198,13 @@ def dc_eigh(dT, eT, stats=None):
     lam[:-1] -= np.abs(eT)
     lam[1:] -= np.abs(eT)
     Q = np.eye(d, dtype=F)
-    for rs in _levels(d):
+    for li, rs in enumerate(_levels(d)):
         for (lo, p, hi) in rs:
-            merge(lam, Q, lo, p, hi, eT[p - 1], stats)
+            if li == 0 and closed_form_level1:
+                assert hi - lo == 2 and p == lo + 1
+                merge2_closed_form(lam, Q, lo, eT[p - 1])
+            else:
+                merge(lam, Q, lo, p, hi, eT[p - 1], stats)
     return lam, Q
 
 

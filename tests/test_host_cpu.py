@@ -343,3 +343,24 @@ def test_dc_emulation_tridiagonal_eigensolver_is_accurate_in_fp32():
     for name, (dT, eT) in cases.items():
         res, orth, ev, _ = check(dT, eT)
         assert res < 2e-6 and orth < 2e-6 and ev < 2e-6, (name, res, orth, ev)
+
+
+def test_dc_closed_form_first_level_equals_the_secular_merge():
+    """csrc/dc_kernels.cu solves the first merge level (2 x 2 blocks) by one Jacobi rotation instead of the secular
+    machinery (tests/dc_emulation.py::merge2_closed_form): same eigenpairs as the generic merge, including negative and
+    zero off-diagonals and equal diagonals, and the full solver agrees with and without the shortcut."""
+    from tests.dc_emulation import dc_eigh
+    rng = np.random.default_rng(3)
+    cases = [(rng.normal(size=2) * 3, rng.normal(size=1)) for _ in range(50)]
+    cases += [(np.array([1.0, 1.0]), np.array([0.5])), (np.array([1.0, 1.0]), np.array([-0.5])),
+              (np.array([2.0, -1.0]), np.array([0.0])), (np.array([1.0, 1.0 + 1e-6]), np.array([1e-3]))]
+    for dT, eT in cases:
+        T = np.array([[dT[0], eT[0]], [eT[0], dT[1]]], dtype=np.float64)
+        for cf in (True, False):
+            lam, Q = dc_eigh(dT, eT, closed_form_level1=cf)
+            assert np.abs(T @ Q - Q * lam).max() < 2e-6 * max(1.0, np.abs(T).max()), (dT, eT, cf)
+            assert np.abs(Q.T @ Q - np.eye(2)).max() < 5e-7
+    dT, eT = rng.normal(size=37) * 2, rng.normal(size=36)
+    l1, Q1 = dc_eigh(dT, eT, closed_form_level1=True)
+    l0, Q0 = dc_eigh(dT, eT, closed_form_level1=False)
+    assert np.abs(np.sort(l1) - np.sort(l0)).max() < 5e-6
