@@ -423,7 +423,12 @@ def test_classic_matches_reference_golden_and_oracle(pkg):
         assert it == int(z["iters"][c])
         assert phi.dtype == np.complex128 and phi.shape == (100,)
         assert rel_err(phi, z["phi"][c]) < 1e-12
-    for n, B, dt in [(100, 1000, torch.complex128), (100, 257, torch.complex64), (256, 33, torch.complex128), (7, 5, torch.complex64)]:
+    # complex64 input with even n <= 104 takes the persistent bulk-copy kernel (k_classic_p: tiles of 32 signals, ragged
+    # last tile, more tiles than CTAs), everything else the plain kernels
+    for n, B, dt in [(100, 1000, torch.complex128), (100, 257, torch.complex64), (256, 33, torch.complex128),
+                     (7, 5, torch.complex64), (64, 100, torch.complex64), (104, 33, torch.complex64),
+                     (36, 4097, torch.complex64), (100, 31, torch.complex64), (100, 20011, torch.complex64),
+                     (2, 3, torch.complex64), (106, 40, torch.complex64)]:
         y, b, _, _ = signals.generate(B, Nb=n, Nd=1, seed=n)
         yt, bt = torch.from_numpy(y).to(dt).cuda(), torch.from_numpy(b).to(dt).cuda()
         out = pkg.admm_for_us_batched(yt, bt, rho=0.7, n_iter=5).cpu().numpy()
