@@ -321,11 +321,11 @@ int launch_eig_tail(const Ws& w, int B, int n, int d, int rcap, const float* Pk,
     //   * k_dc (csrc/dc_kernels.cu): fused fp32 divide & conquer, one CTA per signal.  Throughput bound; it has no
     //     serial chain, so it wins whenever the launch stands alone - a call of a single chunk (B <= chunk: latency and
     //     small-batch mode, B = 1: 9.8 -> 4.4 ms for K = 10) and the eigh tap of the training path
-    //     (measured on B200, d = 101: 0.12 ms against 0.93 ms at B = 1, 1.14 against 4.9 at B = 2368, 7.6 against 9.4
+    //     (measured on B200, d = 101: 0.12 ms against 0.93 ms at B = 1, 1.0 against 4.9 at B = 2368, 6.9 against 9.4
     //     at B = 16384).
     //   * k_ql (fp64 scalar QL chain, one thread per signal, pure latency: 4.1 ms whatever the batch) + k_rotf.  In a
     //     many-chunk forward k_ql runs on the priority lane underneath the other chunk's kernels, which makes this
-    //     pair 6 % faster end to end (84.0k against 79.0k signals/s), so chunks of a larger batch keep it.
+    //     pair 1 % faster end to end (84.1k against 83.1k signals/s), so chunks of a larger batch keep it.
     // ADMMNET_DCK = 1 / 0 forces one form; ADMMNET_DC = 1..3 adds k_merge levels to the QL form (legacy).
     static const int dck_env = getenv("ADMMNET_DCK") ? atoi(getenv("ADMMNET_DCK")) : -1;
     const bool use_dck = dck_env >= 0 ? dck_env != 0 : lone;
