@@ -69,6 +69,43 @@ def test_training_graph_gradients_match_reference_cpu():
     _compare_grads(model, grads, 2e-3)
 
 
+def test_eval_mode_lazy_backward_wiring_cpu(monkeypatch):
+    """admm_net._FusedForward (eval mode with grad enabled): the values come from the fast path, backward re-runs the
+    differentiable graph.  CPU wiring test: the fused kernels are stood in for by the oracle's forward and the CUDA
+    eigen-solver by torch.linalg.eigh, so only the autograd plumbing is exercised - grad_fn on the result, gradients
+    equal to the train-mode graph's (the reference's autograd, golden vectors), input gradients, nothing saved under
+    no_grad."""
+    from admmnet_b200 import admm_net, autograd
+    from admmnet_b200.autograd import PhiAlignmentLoss
+    from oracle import net_oracle
+    z, sd, grads = _load()
+    K = int(z["K"])
+    model = _model(sd, K).eval()
+    y, b, s, pt = (torch.from_numpy(z[k]) for k in ("y", "b", "sigma", "phi_true"))
+    monkeypatch.setattr(autograd, "_cuda_eigh", _cpu_eigh)
+    monkeypatch.setattr(admm_net.PhiEstADMMNet, "_prep", lambda self, y_, b_, s_: (y_, b_, s_.reshape(-1), None))
+    calls = []
+
+    def fake_forward_device(self, y_, b_, s_, out=None):
+        calls.append(1)
+        with torch.no_grad():
+            return net_oracle.forward(self.state_dict(), y_, b_, s_, 10, 10, K)
+    monkeypatch.setattr(admm_net.PhiEstADMMNet, "forward_device", fake_forward_device)
+    phi = model(y, b, s)
+    assert phi.requires_grad and phi.grad_fn is not None and len(calls) == 1
+    assert np.abs(phi.detach().numpy() - z["phi"]).max() < 1e-4 * np.abs(z["phi"]).max()
+    loss, _ = PhiAlignmentLoss()(phi, pt)
+    loss.backward()
+    assert len(calls) == 1                                   # backward rebuilt the graph, it did not call the fast path
+    _compare_grads(model, grads, 2e-3)
+    yg = y.clone().requires_grad_(True)
+    model(yg, b, s).abs().sum().backward()
+    assert yg.grad is not None and float(yg.grad.abs().max()) > 0
+    with torch.no_grad():
+        out = model(y, b, s)
+    assert not out.requires_grad and out.grad_fn is None
+
+
 def test_training_path_refuses_cpu_tensors():
     from admmnet_b200 import _capi
     from admmnet_b200.autograd import BatchedEigh
