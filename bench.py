@@ -443,6 +443,19 @@ def measure_extras(pkg, dev):
                       "ms": ms, "coarse_surface_gflops": flop * Bp / (ms * 1e-3) / 1e9})
         del phi
     out["peak_search_sweep"] = sweep
+    # configs[3], net forward: matrix orders above 128 run the size-agnostic Jacobi layer kernel (k_big_layer) - a
+    # correctness path (~40x the flops of the Householder pipeline), timed here so that the sweep has a forward figure
+    big = []
+    for nb, Bb in ((12, 592), (14, 296), (16, 296)):          # 2 | 1 | 1 signals per persistent CTA (grid 296)
+        torch.manual_seed(0)
+        netb = pkg.PhiEstADMMNet(nb, nb, 3, K_LAYERS).eval()
+        yb_, bb_, sb_ = pkg.generate_signals(Bb, nb, nb, 3, snr_w=20.0, snr_demod=7.0, seed=7, device=dev)
+        netb.forward_device(yb_, bb_, sb_)
+        ms = _time_ms(lambda: netb.forward_device(yb_, bb_, sb_), 1)
+        big.append({"n": nb * nb, "batch": Bb, "K": K_LAYERS, "signals_per_s": Bb / (ms * 1e-3), "ms": ms,
+                    "kernel": "k_big_layer (cyclic two-sided Jacobi, L2-resident scratch)"})
+        del netb, yb_, bb_, sb_
+    out["net_forward_large_n"] = big
     return out
 
 
